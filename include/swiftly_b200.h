@@ -1,0 +1,117 @@
+/*
+ * swiftly_b200.h -- C ABI of the B200-native SwiFTly facet<->subgrid hot path.
+ *
+ * This is the drop-in boundary: the entry points below are what the reference's
+ * native-backend adapter binds.  In the reference
+ * (ska-sdp-distributed-fourier-transform, src/ska_sdp_exec_swiftly/
+ * fourier_transform/core.py) the adapter class `SwiftlyCoreFunc` (core.py:487-929)
+ * forwards each of the eight SwiFTly primitives to a method of the native object
+ * `ska_sdp_func.fourier_transforms.swiftly.Swiftly(N, yN_size, xM_size, W)`
+ * (core.py:508-510).  Those native methods always transform along the LAST axis
+ * of a 2-D array and receive axis-0 work as strided transposed views
+ * (core.py:577-630).  The functions here take the same information in plain C:
+ * a batch of 1-D "lines" described by a base pointer, a line count, a line
+ * length, and line/element strides -- so a C-ordered 2-D array along axis 1, the
+ * same array along axis 0 (transposed view) and 1-D arrays are all one call.
+ *
+ * All samples are complex128 (interleaved re, im doubles).  Offsets are in image
+ * / grid pixels exactly as in the reference (any integer, taken modulo).
+ * Functions return 0 on success, a negative SWIFTLY_B200_E* code otherwise;
+ * swiftly_b200_last_error() gives the message of the calling thread's last
+ * failure.  A handle is immutable after creation: concurrent calls on
+ * different streams are safe.  There is NO CPU implementation behind this ABI:
+ * if no CUDA device is usable every call fails.
+ */
+#ifndef SWIFTLY_B200_H
+#define SWIFTLY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWIFTLY_B200_OK 0
+#define SWIFTLY_B200_EINVAL (-1)      /* bad argument / shape (Python: ValueError)     */
+#define SWIFTLY_B200_ECUDA (-2)       /* CUDA runtime failure (Python: RuntimeError)   */
+#define SWIFTLY_B200_EUNSUPPORTED (-3) /* FFT size not supported by this build          */
+
+#define SWIFTLY_B200_DEVICE 0 /* `data` is a device pointer (cudaMalloc / torch)  */
+#define SWIFTLY_B200_HOST 1   /* `data` is a host pointer; the library stages it  */
+
+typedef struct swiftly_b200 swiftly_b200; /* opaque plan: tables live on one device */
+
+/* A batch of 1-D lines of complex128 samples.
+ * sample (line l, index i) lives at data[(l * line_stride + i * elem_stride)] (complex elements). */
+typedef struct swiftly_b200_lines {
+    void* data;
+    int64_t n_lines;
+    int64_t size;
+    int64_t line_stride;
+    int64_t elem_stride;
+    int32_t location; /* SWIFTLY_B200_DEVICE or SWIFTLY_B200_HOST */
+} swiftly_b200_lines;
+
+/* Plan creation.  Replaces `Swiftly(N, yN_size, xM_size, W)` (core.py:508-510) and
+ * `SwiftlyCore.__init__` / `check_params` (core.py:39-74).  Fb (yN_size-1 doubles,
+ * core.py:104-108) and Fn (xM_size*yN_size/N doubles, core.py:110-117) are the
+ * PSWF-derived window tables computed by the caller with the reference's scipy
+ * formula (core.py:119-150); they are copied to the device.
+ * Parameter violations (N % yN, N % xM, xM*yN % N) return SWIFTLY_B200_EINVAL. */
+int swiftly_b200_create(double W, int64_t N, int64_t xM_size, int64_t yN_size,
+                        const double* Fb, const double* Fn, int device, swiftly_b200** plan);
+void swiftly_b200_destroy(swiftly_b200* plan);
+const char* swiftly_b200_last_error(void);
+/* Library identification: "swiftly_b200 <version> cuda sm_100a" (or "... EMULATED" for
+ * the test-only host build, which the product never loads). */
+const char* swiftly_b200_build_info(void);
+
+int64_t swiftly_b200_contribution_size(const swiftly_b200* plan); /* xM_yN_size, core.py:48 */
+
+/* ---- facet -> subgrid ------------------------------------------------------------ */
+/* SwiftlyCore.prepare_facet (core.py:189-222) / Swiftly.prepare_facet (core.py:684-692).
+ * in: n_lines x facet_size, out: n_lines x yN_size (overwritten). */
+int swiftly_b200_prepare_facet(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                               const swiftly_b200_lines* out, int64_t facet_off, void* stream);
+/* SwiftlyCore.extract_from_facet (core.py:224-253) / Swiftly.extract_from_facet (:713-721).
+ * in: n_lines x yN_size, out: n_lines x xM_yN_size (overwritten). */
+int swiftly_b200_extract_from_facet(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                                    const swiftly_b200_lines* out, int64_t subgrid_off,
+                                    void* stream);
+/* SwiftlyCore.add_to_subgrid (core.py:255-285) / Swiftly.add_to_subgrid (:742-750).
+ * in: n_lines x xM_yN_size, out: n_lines x xM_size, ACCUMULATED into (out +=). */
+int swiftly_b200_add_to_subgrid(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                                const swiftly_b200_lines* out, int64_t facet_off, void* stream);
+/* One axis of SwiftlyCore.finish_subgrid (core.py:287-325) / Swiftly.finish_subgrid
+ * (core.py:795-812, called once per axis).  in: n_lines x xM_size, out: n_lines x
+ * subgrid_size (overwritten).  mask: optional subgrid_size doubles on the same
+ * location as `out` data (0/1 mask of api_helper.py:107-111 folded into the store) or NULL. */
+int swiftly_b200_finish_subgrid(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                                const swiftly_b200_lines* out, int64_t subgrid_off,
+                                const double* mask, void* stream);
+
+/* ---- subgrid -> facet ------------------------------------------------------------ */
+/* One axis of SwiftlyCore.prepare_subgrid (core.py:328-368) / Swiftly.prepare_subgrid_inplace
+ * (core.py:837-853).  in: n_lines x subgrid_size, out: n_lines x xM_size (overwritten). */
+int swiftly_b200_prepare_subgrid(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                                 const swiftly_b200_lines* out, int64_t subgrid_off, void* stream);
+/* SwiftlyCore.extract_from_subgrid (core.py:370-406) / Swiftly.extract_from_subgrid (:866-876).
+ * in: n_lines x xM_size, out: n_lines x xM_yN_size (overwritten). */
+int swiftly_b200_extract_from_subgrid(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                                      const swiftly_b200_lines* out, int64_t facet_off,
+                                      void* stream);
+/* SwiftlyCore.add_to_facet (core.py:408-449) / Swiftly.add_to_facet (:890-900).
+ * in: n_lines x xM_yN_size, out: n_lines x yN_size, ACCUMULATED into (out +=). */
+int swiftly_b200_add_to_facet(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                              const swiftly_b200_lines* out, int64_t subgrid_off, void* stream);
+/* SwiftlyCore.finish_facet (core.py:452-484) / Swiftly.finish_facet (:916-926).
+ * in: n_lines x yN_size, out: n_lines x facet_size (overwritten).  mask as in finish_subgrid
+ * (api_helper.py:175-176, 195-196) or NULL. */
+int swiftly_b200_finish_facet(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                              const swiftly_b200_lines* out, int64_t facet_off,
+                              const double* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIFTLY_B200_H */

@@ -1,0 +1,325 @@
+"""
+``SwiftlyCoreB200`` -- the eight SwiFTly processing primitives on a B200.
+
+Drop-in for the reference's core objects (``SwiftlyCore`` numpy backend,
+``fourier_transform/core.py:20-484`` and ``SwiftlyCoreFunc`` native adapter,
+``core.py:487-929``): same constructor ``(W, N, xM_size, yN_size)``, same
+attributes and properties, same method names, argument meaning and error
+behaviour.  Every method forwards to the hand-written CUDA kernels behind the C
+ABI of ``include/swiftly_b200.h`` -- there is no numpy implementation in here
+and no fallback.
+
+Arrays may be
+  * ``numpy.ndarray`` (host): the library stages them through device memory
+    (H2D, kernel, D2H) -- this is the mode the reference's unit tests use; or
+  * ``torch.Tensor`` on a CUDA device (complex128): used in place on the
+    current torch stream, results are device tensors -- the fast path used by
+    ``SwiftlyForward`` / ``SwiftlyBackward``.
+"""
+
+import ctypes
+
+import numpy
+
+from . import _lib
+from .pswf import window_tables
+
+try:  # torch is plumbing (device memory, streams); numpy mode works without it
+    import torch
+except ImportError:  # pragma: no cover
+    torch = None
+
+
+def _is_tensor(a):
+    return torch is not None and isinstance(a, torch.Tensor)
+
+
+class SwiftlyCoreB200:
+    """Streaming distributed Fourier transform primitives, CUDA (sm_100a) backend.
+
+    :param W: PSWF parameter (grid-space support)
+    :param N: total image size
+    :param xM_size: padded subgrid size
+    :param yN_size: padded facet size
+    :param device: CUDA device index (default: torch's current device, else 0)
+    """
+
+    # pylint: disable=too-many-public-methods
+
+    def __init__(self, W, N, xM_size, yN_size, device=None):
+        self.W = W
+        self.N = N
+        self.xM_size = xM_size
+        self.yN_size = yN_size
+        self.check_params()
+        self.xM_yN_size = self.xM_size * self.yN_size // self.N
+        if device is None:
+            device = 0
+            if torch is not None and torch.cuda.is_available():
+                device = torch.cuda.current_device()
+        self.device = int(device)
+        self._lib = _lib.load()
+        Fb, Fn = window_tables(W, N, xM_size, yN_size)
+        self._Fb = Fb
+        self._Fn = Fn
+        plan = ctypes.c_void_p()
+        rc = self._lib.swiftly_b200_create(
+            float(W), int(N), int(xM_size), int(yN_size),
+            Fb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            Fn.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            self.device, ctypes.byref(plan),
+        )
+        _lib.check(self._lib, rc)
+        self._plan = plan
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None and plan.value:
+            try:
+                self._lib.swiftly_b200_destroy(plan)
+            except Exception:  # pylint: disable=broad-except
+                pass
+            self._plan = None
+
+    # pickle support like SwiftlyCoreFunc (core.py:513-525): rebuild from parameters
+    def __getstate__(self):
+        return {"W": self.W, "N": self.N, "xM_size": self.xM_size,
+                "yN_size": self.yN_size, "device": self.device}
+
+    def __setstate__(self, state):
+        self.__init__(**state)
+
+    def check_params(self):
+        """Validate parameters (core.py:55-74)."""
+        if self.N % self.yN_size != 0:
+            raise ValueError(
+                f"Image size {self.N} not divisible by facet size {self.yN_size}!"
+            )
+        if self.N % self.xM_size != 0:
+            raise ValueError(
+                f"Image size {self.N} not divisible by subgrid size {self.xM_size}!"
+            )
+        if (self.xM_size * self.yN_size) % self.N != 0:
+            raise ValueError(
+                f"Contribution size not integer with image size {self.N}, "
+                f"subgrid size {self.xM_size} and facet size {self.yN_size}!"
+            )
+
+    @property
+    def subgrid_off_step(self):
+        """All subgrid offsets must be divisible by this (core.py:76-83)."""
+        return self.N // self.yN_size
+
+    @property
+    def facet_off_step(self):
+        """All facet offsets must be divisible by this (core.py:85-92)."""
+        return self.N // self.xM_size
+
+    def __repr__(self):
+        return (
+            f"{self.__class__.__name__}(W={self.W}, N={self.N}, "
+            f"xM_size={self.xM_size}, yN_size={self.yN_size})"
+        )
+
+    # ------------------------------------------------------------------ plumbing
+    @staticmethod
+    def _as_complex(a):
+        """Promote input to complex128 (core.py:581-585 promotes real input)."""
+        if _is_tensor(a):
+            if a.dtype != torch.complex128:
+                a = a.to(torch.complex128)
+            return a
+        a = numpy.asarray(a)
+        if a.dtype != numpy.complex128 or not a.flags.c_contiguous:
+            a = numpy.ascontiguousarray(a, dtype=numpy.complex128)
+        return a
+
+    @staticmethod
+    def _new(like, shape, zero):
+        if _is_tensor(like):
+            fn = torch.zeros if zero else torch.empty
+            return fn(tuple(shape), dtype=torch.complex128, device=like.device)
+        fn = numpy.zeros if zero else numpy.empty
+        return fn(tuple(shape), dtype=numpy.complex128)
+
+    @staticmethod
+    def _describe(a, axis):
+        """``swiftly_b200_lines`` for the 1-D lines of ``a`` along ``axis``."""
+        tensor = _is_tensor(a)
+        if tensor:
+            shape = tuple(a.shape)
+            strides = tuple(a.stride())
+            ptr = a.data_ptr()
+            loc = _lib.DEVICE
+        else:
+            shape = a.shape
+            if any(s % a.itemsize for s in a.strides):
+                raise ValueError("array strides must be multiples of the item size")
+            strides = tuple(s // a.itemsize for s in a.strides)
+            ptr = a.ctypes.data
+            loc = _lib.HOST
+        if len(shape) == 1:
+            return _lib.Lines(ptr, 1, shape[0], shape[0] * max(strides[0], 1), strides[0], loc)
+        other = 1 - axis
+        return _lib.Lines(ptr, shape[other], shape[axis], strides[other], strides[axis], loc)
+
+    @staticmethod
+    def _stream(a):
+        if _is_tensor(a):
+            return ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+        return ctypes.c_void_p(0)
+
+    def _mask_ptr(self, mask, like, keep):
+        """Pointer to a float64 mask living where ``like`` lives (or NULL)."""
+        if mask is None:
+            return ctypes.c_void_p(0)
+        if _is_tensor(like):
+            if not _is_tensor(mask):
+                mask = torch.as_tensor(numpy.asarray(mask, dtype=float), device=like.device)
+            mask = mask.to(torch.float64).contiguous()
+            keep.append(mask)
+            return ctypes.c_void_p(mask.data_ptr())
+        mask = numpy.ascontiguousarray(mask, dtype=float)
+        keep.append(mask)
+        return ctypes.c_void_p(mask.ctypes.data)
+
+    def _run(self, fn_name, in_arr, out_size, axis, out, offset, accumulate=False, mask=None):
+        """Shape handling shared by all primitives.
+
+        Mirrors ``SwiftlyCoreFunc._auto_broadcast_create`` (core.py:577-630):
+        1-D or 2-D input, the transformed axis changes length to ``out_size``,
+        ``out`` is created (zeros for accumulating primitives, core.py:742-750)
+        or shape-checked (``ValueError``).
+        """
+        in_arr = self._as_complex(in_arr)
+        dims = len(in_arr.shape)
+        if dims == 1:
+            shape = (out_size,)
+            axis = 0
+        elif dims == 2:
+            if axis not in (0, 1):
+                raise ValueError(f"Invalid axis {axis} for shape {tuple(in_arr.shape)}!")
+            shape = list(in_arr.shape)
+            shape[axis] = out_size
+            shape = tuple(shape)
+        else:
+            raise ValueError(
+                f"Invalid number of dimensions in input array: {tuple(in_arr.shape)}"
+            )
+        if out is None:
+            out = self._new(in_arr, shape, zero=accumulate)
+        else:
+            if tuple(out.shape) != shape:
+                raise ValueError(
+                    f"Output array has shape {tuple(out.shape)}, expected {shape}!"
+                )
+            if _is_tensor(out) != _is_tensor(in_arr):
+                raise ValueError("input and output must both be numpy arrays or CUDA tensors")
+            if _is_tensor(out):
+                if out.dtype != torch.complex128:
+                    raise ValueError("output tensor must be complex128")
+            elif out.dtype != numpy.complex128:
+                raise ValueError("output array must be complex128")
+        if _is_tensor(in_arr) and not in_arr.is_cuda:
+            raise ValueError("tensors must live on a CUDA device (use numpy arrays for host data)")
+        din = self._describe(in_arr, axis)
+        dout = self._describe(out, axis)
+        keep = []
+        args = [self._plan, ctypes.byref(din), ctypes.byref(dout), int(offset)]
+        if fn_name in ("swiftly_b200_finish_subgrid", "swiftly_b200_finish_facet"):
+            args.append(self._mask_ptr(mask, out, keep))
+        args.append(self._stream(in_arr))
+        rc = getattr(self._lib, fn_name)(*args)
+        _lib.check(self._lib, rc)
+        return out
+
+    # ------------------------------------------------------------------ facet -> subgrid
+    def prepare_facet(self, facet, facet_off, axis, out=None):
+        """Prepare facet for extracting subgrid contributions (core.py:189-222)."""
+        return self._run("swiftly_b200_prepare_facet", facet, self.yN_size, axis, out, facet_off)
+
+    def extract_from_facet(self, prep_facet, subgrid_off, axis, out=None):
+        """Extract the facet contribution to a subgrid (core.py:224-253)."""
+        return self._run(
+            "swiftly_b200_extract_from_facet", prep_facet, self.xM_yN_size, axis, out, subgrid_off
+        )
+
+    def add_to_subgrid(self, facet_contrib, facet_off, axis, out=None):
+        """Transform a facet contribution and ADD it to ``out`` (core.py:255-285)."""
+        return self._run(
+            "swiftly_b200_add_to_subgrid", facet_contrib, self.xM_size, axis, out, facet_off,
+            accumulate=True,
+        )
+
+    def add_to_subgrid_2d(self, facet_contrib, facet_off0, facet_off1, out=None):
+        """Both axes of ``add_to_subgrid`` at once (SwiftlyCoreFunc, core.py:752-778)."""
+        facet_contrib = self._as_complex(facet_contrib)
+        if len(facet_contrib.shape) != 2:
+            raise ValueError(
+                f"Invalid number of dimensions in input array: {tuple(facet_contrib.shape)}"
+            )
+        shape = (self.xM_size, self.xM_size)
+        if out is not None and tuple(out.shape) != shape:
+            raise ValueError(f"Output array has shape {tuple(out.shape)}, expected {shape}!")
+        tmp = self.add_to_subgrid(facet_contrib, facet_off0, axis=0)
+        return self.add_to_subgrid(tmp, facet_off1, axis=1, out=out)
+
+    def finish_subgrid(self, summed_contribs, subgrid_off, subgrid_size, out=None, masks=None):
+        """Finish a subgrid on all axes (core.py:287-325).
+
+        ``masks``: optional per-axis 0/1 vectors folded into the final store
+        (what ``sum_and_finish_subgrid`` multiplies afterwards, api_helper.py:107-111).
+        """
+        dims = len(summed_contribs.shape)
+        if not isinstance(subgrid_off, (list, tuple)):
+            if dims != 1:
+                raise ValueError("Subgrid offset must be given for every dimension!")
+            subgrid_off = [subgrid_off]
+        if len(subgrid_off) != dims:
+            raise ValueError("Subgrid offset must be given for every dimension!")
+        if masks is None:
+            masks = [None] * dims
+        fn = "swiftly_b200_finish_subgrid"
+        if dims == 1:
+            return self._run(fn, summed_contribs, subgrid_size, 0, out, subgrid_off[0],
+                             mask=masks[0])
+        if dims != 2:
+            raise ValueError(f"Invalid shape {tuple(summed_contribs.shape)}!")
+        # contiguous axis first on the big array, strided axis on the smaller result
+        tmp = self._run(fn, summed_contribs, subgrid_size, 1, None, subgrid_off[1], mask=masks[1])
+        return self._run(fn, tmp, subgrid_size, 0, out, subgrid_off[0], mask=masks[0])
+
+    # ------------------------------------------------------------------ subgrid -> facet
+    def prepare_subgrid(self, subgrid, subgrid_off, out=None):
+        """Pad, align and Fourier transform a subgrid on all axes (core.py:328-368)."""
+        dims = len(subgrid.shape)
+        if dims == 1 and not isinstance(subgrid_off, (list, tuple)):
+            subgrid_off = (subgrid_off,)
+        if len(subgrid_off) != dims:
+            raise ValueError("Dimensionality mismatch between subgrid and offsets!")
+        fn = "swiftly_b200_prepare_subgrid"
+        if dims == 1:
+            return self._run(fn, subgrid, self.xM_size, 0, out, subgrid_off[0])
+        if dims != 2:
+            raise ValueError(f"Invalid shape {tuple(subgrid.shape)}!")
+        tmp = self._run(fn, subgrid, self.xM_size, 0, None, subgrid_off[0])
+        return self._run(fn, tmp, self.xM_size, 1, out, subgrid_off[1])
+
+    def extract_from_subgrid(self, FSi, facet_off, axis, out=None):
+        """Extract the contribution of a subgrid to a facet (core.py:370-406)."""
+        return self._run(
+            "swiftly_b200_extract_from_subgrid", FSi, self.xM_yN_size, axis, out, facet_off
+        )
+
+    def add_to_facet(self, subgrid_contrib, subgrid_off, axis, out=None):
+        """ADD a subgrid contribution to a facet accumulator (core.py:408-449)."""
+        return self._run(
+            "swiftly_b200_add_to_facet", subgrid_contrib, self.yN_size, axis, out, subgrid_off,
+            accumulate=True,
+        )
+
+    def finish_facet(self, MiNjSi_sum, facet_off, facet_size, axis, out=None, mask=None):
+        """Finish a facet along one axis (core.py:452-484); optional 0/1 ``mask``."""
+        return self._run(
+            "swiftly_b200_finish_facet", MiNjSi_sum, facet_size, axis, out, facet_off, mask=mask
+        )

@@ -1,0 +1,15 @@
+// SwiFTly B200 -- size dispatch of extract_from_subgrid (one translation unit per primitive keeps
+// the heavy FP64 template instantiations compiling in parallel).
+#include "dispatch.cuh"
+
+namespace swiftly {
+
+int run_extract_from_subgrid(const swiftly_b200* h, const ExtractFromSubgridOp& op, bool lf, cudaStream_t s) {
+    const int n = op.m;
+    switch (n) {
+        SW_DIRECT_CASES(+1, ExtractFromSubgridOp)
+        default: return unsupported(n);
+    }
+}
+
+}  // namespace swiftly

@@ -1,0 +1,201 @@
+// SwiFTly B200 -- in-CTA complex128 FFT engine.
+//
+// One "line" (a 1-D transform of N complex128 samples, N a power of two,
+// 16 <= N <= 8192) is transformed by T = N/16 threads with the Stockham
+// autosort algorithm: radix-16 passes (and one final radix-2/4/8 pass when
+// log2 N is not a multiple of 4).  Each pass holds its 16 samples in
+// registers, the exchange between passes goes through shared memory
+// (padded by one 16-byte slot per 16 to make the stride-16 scatter of the
+// first pass conflict free).  The FIRST pass reads its input through a
+// caller-supplied loader functor (global memory gather: window multiply,
+// zero padding and cyclic shifts are index arithmetic there) and the LAST
+// pass hands its output to a storer functor (scatter / accumulate / window
+// multiply), so a line makes exactly one trip HBM -> registers -> HBM.
+//
+// Twiddles come from a per-size table W_N^t = exp(-2 pi i t / N), t < N, in
+// global memory (L1/L2 resident, read through the read-only path); the
+// inverse direction conjugates on the fly.  The first pass needs none.
+//
+// Lines of 2N samples that do not fit shared memory (yN = 16384) are done as
+// two N-point transforms after one decimation-in-frequency radix-2 step that
+// is folded into the loader (split2_*), see kernels.cuh.
+#pragma once
+
+#include "common.cuh"
+
+namespace swiftly {
+
+// ---------------------------------------------------------------- radix kernels
+// v * (c + i * DIR * s)
+template <int DIR>
+SW_HD cplx mul_w(cplx v, double c, double s) {
+    return DIR < 0 ? mk(v.x * c + v.y * s, v.y * c - v.x * s)
+                   : mk(v.x * c - v.y * s, v.y * c + v.x * s);
+}
+
+template <int DIR>
+SW_HD void bfly2(cplx& a, cplx& b) {
+    cplx t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+// in-place 4-point DFT, natural order
+template <int DIR>
+SW_HD void bfly4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+    cplx t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    cplx t2 = cadd(a1, a3), t3 = mul_i<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+#define SW_SQRT1_2 0.70710678118654752440
+#define SW_COS_PI_8 0.92387953251128673848
+#define SW_SIN_PI_8 0.38268343236508978178
+
+template <int R, int DIR>
+struct Radix;
+
+template <int DIR>
+struct Radix<2, DIR> {
+    static SW_HD void run(cplx* v) { bfly2<DIR>(v[0], v[1]); }
+};
+
+template <int DIR>
+struct Radix<4, DIR> {
+    static SW_HD void run(cplx* v) { bfly4<DIR>(v[0], v[1], v[2], v[3]); }
+};
+
+template <int DIR>
+struct Radix<8, DIR> {
+    // j = c + 2a, k = a' + 4c'
+    static SW_HD void run(cplx* v) {
+        bfly4<DIR>(v[0], v[2], v[4], v[6]);
+        bfly4<DIR>(v[1], v[3], v[5], v[7]);
+        v[3] = mul_w<DIR>(v[3], SW_SQRT1_2, SW_SQRT1_2);
+        v[5] = mul_i<DIR>(v[5]);
+        v[7] = mul_w<DIR>(v[7], -SW_SQRT1_2, SW_SQRT1_2);
+        cplx x0 = cadd(v[0], v[1]), x4 = csub(v[0], v[1]);
+        cplx x1 = cadd(v[2], v[3]), x5 = csub(v[2], v[3]);
+        cplx x2 = cadd(v[4], v[5]), x6 = csub(v[4], v[5]);
+        cplx x3 = cadd(v[6], v[7]), x7 = csub(v[6], v[7]);
+        v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
+        v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
+    }
+};
+
+template <int DIR>
+struct Radix<16, DIR> {
+    // j = c + 4a, k = a' + 4c'
+    static SW_HD void run(cplx* v) {
+        bfly4<DIR>(v[0], v[4], v[8], v[12]);
+        bfly4<DIR>(v[1], v[5], v[9], v[13]);
+        bfly4<DIR>(v[2], v[6], v[10], v[14]);
+        bfly4<DIR>(v[3], v[7], v[11], v[15]);
+        // v[c + 4a'] *= W16^(c a')
+        v[5] = mul_w<DIR>(v[5], SW_COS_PI_8, SW_SIN_PI_8);     // 1
+        v[9] = mul_w<DIR>(v[9], SW_SQRT1_2, SW_SQRT1_2);       // 2
+        v[13] = mul_w<DIR>(v[13], SW_SIN_PI_8, SW_COS_PI_8);   // 3
+        v[6] = mul_w<DIR>(v[6], SW_SQRT1_2, SW_SQRT1_2);       // 2
+        v[10] = mul_i<DIR>(v[10]);                             // 4
+        v[14] = mul_w<DIR>(v[14], -SW_SQRT1_2, SW_SQRT1_2);    // 6
+        v[7] = mul_w<DIR>(v[7], SW_SIN_PI_8, SW_COS_PI_8);     // 3
+        v[11] = mul_w<DIR>(v[11], -SW_SQRT1_2, SW_SQRT1_2);    // 6
+        v[15] = mul_w<DIR>(v[15], -SW_COS_PI_8, -SW_SIN_PI_8); // 9
+        bfly4<DIR>(v[0], v[1], v[2], v[3]);
+        bfly4<DIR>(v[4], v[5], v[6], v[7]);
+        bfly4<DIR>(v[8], v[9], v[10], v[11]);
+        bfly4<DIR>(v[12], v[13], v[14], v[15]);
+        // now v[c' + 4a'] = X[a' + 4c']: transpose the 4x4
+        cplx t;
+        t = v[1]; v[1] = v[4]; v[4] = t;
+        t = v[2]; v[2] = v[8]; v[8] = t;
+        t = v[3]; v[3] = v[12]; v[12] = t;
+        t = v[6]; v[6] = v[9]; v[9] = t;
+        t = v[7]; v[7] = v[13]; v[13] = t;
+        t = v[11]; v[11] = v[14]; v[14] = t;
+    }
+};
+
+// ---------------------------------------------------------------- plan
+template <int N>
+struct FftCfg {
+    static_assert(N >= 16 && (N & (N - 1)) == 0, "FFT size must be a power of two >= 16");
+    static constexpr int T = N / 16;           // threads per line
+    static constexpr int PADDED = N + N / 16;  // smem slots (16 B each) per line
+};
+
+SW_HD int sm_phys(int a) { return a + (a >> 4); }
+
+template <int N, int NS>
+struct PassRadix {
+    static constexpr int R = (N / NS >= 16) ? 16 : (N / NS);
+};
+
+// Stockham passes from sub-transform size NS up to N (recursive over passes).
+//   lt  : thread index within the line group, 0 <= lt < T
+//   sm  : this line's shared memory buffer (FftCfg<N>::PADDED slots)
+//   tw  : table exp(-2 pi i t / N), t < N
+//   ld(q)    -> cplx   natural-order input sample q   (FIRST pass only)
+//   st(p, v)          natural-order output sample p  (LAST pass only)
+//   sync()            CTA barrier
+template <int N, int NS, int DIR, class Ld, class St, class Sync>
+SW_HD void stockham_passes(int lt, cplx* sm, const cplx* tw, Ld& ld, St& st, Sync& sync) {
+    constexpr int T = FftCfg<N>::T;
+    constexpr int R = PassRadix<N, NS>::R;
+    constexpr int NB = N / R;  // butterflies in this pass
+    constexpr bool FIRST = (NS == 1);
+    constexpr bool LAST = (NS * R == N);
+    constexpr int ITERS = NB / T;  // NB = N/R >= N/16 = T, both powers of two
+    cplx v[ITERS][R];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = lt + it * T;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (FIRST)
+                v[it][r] = ld(j + r * NB);
+            else
+                v[it][r] = sm[sm_phys(j + r * NB)];
+        }
+    }
+    if (!FIRST && !LAST) sync();  // everybody has read before anybody overwrites
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = lt + it * T;
+        if (!FIRST) {
+            const int k = j & (NS - 1);
+            constexpr int TSTRIDE = N / (NS * R);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                cplx w = ldg_c(tw + r * k * TSTRIDE);
+                if (DIR > 0) w.y = -w.y;
+                v[it][r] = cmul(v[it][r], w);
+            }
+        }
+        Radix<R, DIR>::run(v[it]);
+        const int base = (j / NS) * (NS * R) + (j & (NS - 1));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (LAST)
+                st(base + r * NS, v[it][r]);
+            else
+                sm[sm_phys(base + r * NS)] = v[it][r];
+        }
+    }
+    if constexpr (!LAST) {
+        sync();
+        stockham_passes<N, NS * R, DIR>(lt, sm, tw, ld, st, sync);
+    }
+}
+
+// Full N-point transform of one line.  The caller guarantees that nobody is
+// still reading `sm` from a previous line (sync before re-use).
+template <int N, int DIR, class Ld, class St, class Sync>
+SW_HD void line_fft(int lt, cplx* sm, const cplx* tw, Ld& ld, St& st, Sync& sync) {
+    stockham_passes<N, 1, DIR>(lt, sm, tw, ld, st, sync);
+}
+
+}  // namespace swiftly

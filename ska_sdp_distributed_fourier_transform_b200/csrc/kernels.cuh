@@ -1,0 +1,278 @@
+// SwiFTly B200 -- kernel bodies for the eight SwiFTly primitives.
+//
+// Every primitive is "a batch of independent 1-D lines": the Python/C caller
+// passes a line stride and an element stride (in complex128 elements) for input
+// and output, so `axis=0` and `axis=1` of a C-ordered 2-D array, 1-D arrays and
+// strided (transposed) views are all the same kernel.  pad / extract / roll /
+// fftshift of the reference (core.py, fourier_algorithm.py) are closed-form
+// modular index maps inside the loader / storer functors of the FFT engine;
+// nothing but the FFT input is read and nothing but the result is written.
+//
+// Centred transforms: fft_c(x) = fftshift(FFT(ifftshift(x))) -- for even n both
+// shifts are a cyclic rotation by n/2, so natural FFT index q' corresponds to
+// centred index (q' + n/2) mod n on input and output alike
+// (fourier_algorithm.py:96-122).
+#pragma once
+
+#include "fft_engine.cuh"
+
+namespace swiftly {
+
+struct Lines {
+    const cplx* in;
+    cplx* out;
+    int64_t in_ls, in_es;    // input line stride / element stride (elements)
+    int64_t out_ls, out_es;  // output line stride / element stride
+    int64_t n_lines;
+};
+
+SW_HD int wrap_add(int a, int b, int n) {  // (a + b) mod n for 0 <= a,b < n
+    int r = a + b;
+    return r >= n ? r - n : r;
+}
+SW_HD int wrap_sub(int a, int b, int n) {  // (a - b) mod n for 0 <= a,b < n
+    int r = a - b;
+    return r < 0 ? r + n : r;
+}
+
+// ------------------------------------------------------------------ ops
+// prepare_facet (core.py:189-222): out = ifft_c(roll(pad_mid(facet * Fb_c, yN), facet_off))
+struct PrepareFacetOp {
+    Lines g;
+    const double* fb;  // Fb window already offset: fb[k] = Fb_c[k], k < fs
+    int n;             // yN
+    int fs;            // facet size along the axis
+    int shift_in;      // k = (q' + shift_in) mod n  with shift_in = (fs//2 - facet_off) mod n
+    double scale;      // 1 / yN
+    SW_HD cplx load(int64_t line, int q) const {
+        int k = wrap_add(q, shift_in, n);
+        if (k >= fs) return mk(0.0, 0.0);
+        return cscale(ldg_c(g.in + line * g.in_ls + (int64_t)k * g.in_es), ldg_d(fb + k));
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        int pc = wrap_add(p, n / 2, n);
+        g.out[line * g.out_ls + (int64_t)pc * g.out_es] = cscale(v, scale);
+    }
+};
+
+// finish_facet (core.py:452-484): out[k] = Fb_c[k] * fft_c(sum)[(yN/2 - fs//2 + k + off) mod yN]
+struct FinishFacetOp {
+    Lines g;
+    const double* fb;
+    int n, fs;
+    int start;  // (yN/2 - fs//2 + facet_off) mod yN
+    const double* mask;  // optional 0/1 facet mask along the axis (api_helper.py:175-176,195-196)
+    SW_HD cplx load(int64_t line, int q) const {
+        int qc = wrap_add(q, n / 2, n);
+        return ldg_c(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        int pc = wrap_add(p, n / 2, n);
+        int k = wrap_sub(pc, start, n);
+        if (k < fs) {
+            double s = mask ? ldg_d(fb + k) * ldg_d(mask + k) : ldg_d(fb + k);
+            g.out[line * g.out_ls + (int64_t)k * g.out_es] = cscale(v, s);
+        }
+    }
+};
+
+// add_to_subgrid (core.py:255-285):
+//   out[(xM/2 - m/2 + u + sf) mod xM] += Fn[u] * fft_c(contrib)[(u + sf) mod m]
+struct AddToSubgridOp {
+    Lines g;
+    const double* fn;
+    int m, xM;
+    int sf_m;  // sf mod m
+    int base;  // (xM/2 - m/2 + sf) mod xM
+    SW_HD cplx load(int64_t line, int t) const {
+        int tc = wrap_add(t, m / 2, m);
+        return ldg_c(g.in + line * g.in_ls + (int64_t)tc * g.in_es);
+    }
+    SW_HD void store(int64_t line, int w, cplx v) const {
+        int wc = wrap_add(w, m / 2, m);
+        int u = wrap_sub(wc, sf_m, m);
+        int pos = wrap_add(base, u, xM);
+        cplx* o = g.out + line * g.out_ls + (int64_t)pos * g.out_es;
+        cplx a = *o;
+        double f = ldg_d(fn + u);
+        *o = mk(a.x + f * v.x, a.y + f * v.y);
+    }
+};
+
+// extract_from_subgrid (core.py:370-406):
+//   w[(u + sf) mod m] = Fn[u] * FSi[(xM/2 - m/2 + u + sf) mod xM];  out = ifft_c(w)
+struct ExtractFromSubgridOp {
+    Lines g;
+    const double* fn;
+    int m, xM;
+    int sf_m, base;
+    double scale;  // 1 / m
+    SW_HD cplx load(int64_t line, int t) const {
+        int tc = wrap_add(t, m / 2, m);
+        int u = wrap_sub(tc, sf_m, m);
+        int pos = wrap_add(base, u, xM);
+        return cscale(ldg_c(g.in + line * g.in_ls + (int64_t)pos * g.in_es), ldg_d(fn + u));
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        int pc = wrap_add(p, m / 2, m);
+        g.out[line * g.out_ls + (int64_t)pc * g.out_es] = cscale(v, scale);
+    }
+};
+
+// finish_subgrid, one axis (core.py:287-325):
+//   out[r] = ifft_c(summed)[(xM/2 - sz//2 + r + off) mod xM]
+struct FinishSubgridOp {
+    Lines g;
+    int xM, sz;
+    int start;  // (xM/2 - sz//2 + off) mod xM
+    double scale;  // 1 / xM
+    const double* mask;  // optional 0/1 mask along the axis (api_helper.py:107-111) or null
+    SW_HD cplx load(int64_t line, int q) const {
+        int qc = wrap_add(q, xM / 2, xM);
+        return ldg_c(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        int pc = wrap_add(p, xM / 2, xM);
+        int r = wrap_sub(pc, start, xM);
+        if (r < sz) {
+            double s = mask ? scale * ldg_d(mask + r) : scale;
+            g.out[line * g.out_ls + (int64_t)r * g.out_es] = cscale(v, s);
+        }
+    }
+};
+
+// prepare_subgrid, one axis (core.py:328-368):
+//   out = fft_c(roll(pad_mid(subgrid, xM), off))
+struct PrepareSubgridOp {
+    Lines g;
+    int xM, sz;
+    int start;  // (xM/2 - sz//2 + off) mod xM
+    SW_HD cplx load(int64_t line, int q) const {
+        int qc = wrap_add(q, xM / 2, xM);
+        int r = wrap_sub(qc, start, xM);
+        if (r >= sz) return mk(0.0, 0.0);
+        return ldg_c(g.in + line * g.in_ls + (int64_t)r * g.in_es);
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        int pc = wrap_add(p, xM / 2, xM);
+        g.out[line * g.out_ls + (int64_t)pc * g.out_es] = v;
+    }
+};
+
+// ------------------------------------------------------------------ line kernels
+// NFFT-point transform of a batch of lines; LPC lines per CTA, T = NFFT/16
+// threads per line.  LINE_FASTEST selects which of (line, thread-in-line) varies
+// fastest across the lanes of a warp: use it when lines are adjacent in memory
+// (axis-0 transforms of C-ordered arrays) so that global accesses coalesce
+// across lines instead of along them.
+template <int NFFT, int DIR, int LPC, bool LINE_FASTEST, class Op>
+struct LineKernel {
+    static constexpr int T = FftCfg<NFFT>::T;
+    static constexpr int THREADS = T * LPC;
+    // odd slot stride between line buffers => lines land in different banks
+    static constexpr int LSTRIDE = FftCfg<NFFT>::PADDED | 1;
+    static constexpr size_t SMEM = (size_t)LSTRIDE * LPC * sizeof(cplx);
+    Op op;
+    const cplx* tw;
+
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        cplx* smem = (cplx*)ctx.smem;
+        const int l = LINE_FASTEST ? (ctx.tid % LPC) : (ctx.tid / T);
+        const int lt = LINE_FASTEST ? (ctx.tid / LPC) : (ctx.tid % T);
+        cplx* sm = smem + (size_t)l * LSTRIDE;
+        auto sync = [&]() { ctx.sync(); };
+        for (int64_t line0 = (int64_t)ctx.bid * LPC; line0 < op.g.n_lines;
+             line0 += (int64_t)ctx.nblocks * LPC) {
+            const int64_t line = line0 + l;
+            const bool active = line < op.g.n_lines;
+            auto ld = [&](int q) { return active ? op.load(line, q) : mk(0.0, 0.0); };
+            auto st = [&](int p, cplx v) {
+                if (active) op.store(line, p, v);
+            };
+            line_fft<NFFT, DIR>(lt, sm, tw, ld, st, sync);
+            ctx.sync();  // smem is reused by the next line
+        }
+    }
+};
+
+// 2*H-point transform as two H-point transforms after one radix-2
+// decimation-in-frequency step folded into the loader:
+//   X[2k]   = FFT_H( z[j] + z[j+H] )[k]
+//   X[2k+1] = FFT_H( (z[j] - z[j+H]) * W_2H^(DIR j) )[k]
+// tw2 is the 2H-point table, tw the H-point table.  One line per CTA.
+template <int H, int DIR, class Op>
+struct SplitLineKernel {
+    static constexpr int T = FftCfg<H>::T;
+    static constexpr int THREADS = T;
+    static constexpr size_t SMEM = (size_t)FftCfg<H>::PADDED * sizeof(cplx);
+    Op op;
+    const cplx* tw;   // size H
+    const cplx* tw2;  // size 2H
+
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        cplx* sm = (cplx*)ctx.smem;
+        const int lt = ctx.tid;
+        auto sync = [&]() { ctx.sync(); };
+        for (int64_t line = ctx.bid; line < op.g.n_lines; line += ctx.nblocks) {
+            {
+                auto ld = [&](int q) { return cadd(op.load(line, q), op.load(line, q + H)); };
+                auto st = [&](int p, cplx v) { op.store(line, 2 * p, v); };
+                line_fft<H, DIR>(lt, sm, tw, ld, st, sync);
+            }
+            ctx.sync();
+            {
+                auto ld = [&](int q) {
+                    cplx w = ldg_c(tw2 + q);
+                    if (DIR > 0) w.y = -w.y;
+                    return cmul(csub(op.load(line, q), op.load(line, q + H)), w);
+                };
+                auto st = [&](int p, cplx v) { op.store(line, 2 * p + 1, v); };
+                line_fft<H, DIR>(lt, sm, tw, ld, st, sync);
+            }
+            ctx.sync();
+        }
+    }
+};
+
+// ------------------------------------------------------------------ gather / scatter kernels
+// extract_from_facet (core.py:224-253):  out[t] = prep[(base + ((t - s_m) mod m)) mod yN]
+// add_to_facet      (core.py:408-449):  out[(base + ((t - s_m) mod m)) mod yN] += contrib[t]
+//   s = subgrid_off * yN // N, s_m = s mod m, base = (yN/2 - m/2 + s) mod yN
+template <bool SCATTER_ADD>
+struct WindowCopyKernel {
+    static constexpr int THREADS = 256;
+    static constexpr size_t SMEM = 0;
+    Lines g;
+    int m, yN, s_m, base;
+    int line_fastest;  // lines adjacent in memory (axis 0): make `line` the fast index
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        const int64_t total = g.n_lines * (int64_t)m;
+        for (int64_t i = (int64_t)ctx.bid * THREADS + ctx.tid; i < total;
+             i += (int64_t)ctx.nblocks * THREADS) {
+            int64_t line;
+            int t;
+            if (line_fastest) {
+                line = i % g.n_lines;
+                t = (int)(i / g.n_lines);
+            } else {
+                line = i / m;
+                t = (int)(i % m);
+            }
+            int w = wrap_add(base, wrap_sub(t, s_m, m), yN);
+            if (SCATTER_ADD) {
+                cplx v = ldg_c(g.in + line * g.in_ls + (int64_t)t * g.in_es);
+                cplx* o = g.out + line * g.out_ls + (int64_t)w * g.out_es;
+                cplx a = *o;
+                *o = cadd(a, v);
+            } else {
+                g.out[line * g.out_ls + (int64_t)t * g.out_es] =
+                    ldg_c(g.in + line * g.in_ls + (int64_t)w * g.in_es);
+            }
+        }
+    }
+};
+
+}  // namespace swiftly

@@ -1,0 +1,46 @@
+// SwiFTly B200 -- plan (handle) definition shared by the C-ABI translation units.
+#pragma once
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../include/swiftly_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+struct swiftly_b200 {
+    double W;
+    int64_t N, xM, yN, m;
+    int device;
+    double* d_Fb;  // yN - 1
+    double* d_Fn;  // m
+    // twiddle tables exp(-2 pi i t / n), t < n, keyed by n
+    mutable std::mutex mu;
+    mutable std::map<int, swiftly::cplx*> tw;
+    int force_split;  // debug / test: transform yN lines with the 2 x yN/2 split path
+};
+
+namespace swiftly {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+// returns the table for size n (creating it on first use), nullptr on failure
+const cplx* twiddles(const swiftly_b200* h, int n);
+
+// largest directly supported power-of-two line length (fits shared memory)
+static const int MAX_DIRECT_FFT = 8192;
+static const int MIN_FFT = 16;
+inline bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// dispatchers, one translation unit each (compile time!): launch `op` over all
+// its lines with an n-point transform.  dir = -1 forward, +1 inverse.
+int run_prepare_facet(const swiftly_b200* h, const PrepareFacetOp& op, bool line_fastest, cudaStream_t s);
+int run_finish_facet(const swiftly_b200* h, const FinishFacetOp& op, bool line_fastest, cudaStream_t s);
+int run_add_to_subgrid(const swiftly_b200* h, const AddToSubgridOp& op, bool line_fastest, cudaStream_t s);
+int run_extract_from_subgrid(const swiftly_b200* h, const ExtractFromSubgridOp& op, bool line_fastest, cudaStream_t s);
+int run_finish_subgrid(const swiftly_b200* h, const FinishSubgridOp& op, bool line_fastest, cudaStream_t s);
+int run_prepare_subgrid(const swiftly_b200* h, const PrepareSubgridOp& op, bool line_fastest, cudaStream_t s);
+
+}  // namespace swiftly

@@ -1,0 +1,160 @@
+// TEST TOOLING ONLY -- host emulation of the tiny slice of the CUDA runtime and
+// execution model that the SwiFTly kernels use, so that the kernel *bodies*
+// (index algebra, FFT passes, barriers) can be exercised by pytest in a
+// container without a GPU.  Each CUDA thread of a CTA runs as a ucontext fibre;
+// __syncthreads() yields to a round-robin scheduler, which reproduces barrier
+// semantics exactly (one sweep = every thread advances to its next barrier).
+// The product library is never built from this header.
+#pragma once
+
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <vector>
+
+struct double2 {
+    double x, y;
+};
+static inline double2 make_double2(double x, double y) {
+    double2 r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum cudaMemcpyKind {
+    cudaMemcpyHostToHost = 0,
+    cudaMemcpyHostToDevice = 1,
+    cudaMemcpyDeviceToHost = 2,
+    cudaMemcpyDeviceToDevice = 3,
+    cudaMemcpyDefault = 4
+};
+
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+    *p = malloc(n ? n : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+static inline cudaError_t cudaFree(void* p) {
+    free(p);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+    memmove(d, s, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    memmove(d, s, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w,
+                                            size_t h, cudaMemcpyKind, cudaStream_t) {
+    for (size_t i = 0; i < h; ++i) memmove((char*)d + i * dp, (const char*)s + i * sp, w);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
+    memset(d, v, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) {
+    *d = 0;
+    return cudaSuccess;
+}
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
+
+namespace swiftly {
+
+struct EmuBlock;
+
+struct HostCtx {
+    int tid, bid, nblocks;
+    char* smem;
+    EmuBlock* blk;
+    inline void sync() const;
+};
+
+struct EmuBlock {
+    ucontext_t main_ctx;
+    std::vector<ucontext_t> ctxs;
+    std::vector<char*> stacks;
+    std::vector<char> done;
+    int current;
+    void (*entry)(void*, HostCtx&);
+    void* body;
+    std::vector<HostCtx> hctx;
+};
+
+static EmuBlock* g_emu_block = nullptr;
+
+inline void HostCtx::sync() const {
+    EmuBlock* b = blk;
+    swapcontext(&b->ctxs[tid], &b->main_ctx);
+}
+
+static void emu_trampoline() {
+    EmuBlock* b = g_emu_block;
+    int t = b->current;
+    b->entry(b->body, b->hctx[t]);
+    b->done[t] = 1;
+    // returning switches to uc_link (main_ctx)
+}
+
+template <class Body>
+static void emu_entry(void* body, HostCtx& ctx) {
+    (*(const Body*)body)(ctx);
+}
+
+template <class Body>
+inline cudaError_t launch_body(const Body& body, int grid, size_t smem_bytes, cudaStream_t) {
+    const int T = Body::THREADS;
+    const size_t STACK = 256 * 1024;
+    EmuBlock blk;
+    blk.ctxs.resize(T);
+    blk.stacks.resize(T);
+    blk.done.resize(T);
+    blk.hctx.resize(T);
+    blk.entry = &emu_entry<Body>;
+    blk.body = (void*)&body;
+    for (int t = 0; t < T; ++t) blk.stacks[t] = (char*)malloc(STACK);
+    char* smem = (char*)malloc(smem_bytes + 64);
+    for (int bid = 0; bid < grid; ++bid) {
+        memset(smem, 0xA5, smem_bytes + 64);  // poison: uninitialised smem reads show up
+        for (int t = 0; t < T; ++t) {
+            getcontext(&blk.ctxs[t]);
+            blk.ctxs[t].uc_stack.ss_sp = blk.stacks[t];
+            blk.ctxs[t].uc_stack.ss_size = STACK;
+            blk.ctxs[t].uc_link = &blk.main_ctx;
+            makecontext(&blk.ctxs[t], (void (*)())emu_trampoline, 0);
+            blk.done[t] = 0;
+            blk.hctx[t].tid = t;
+            blk.hctx[t].bid = bid;
+            blk.hctx[t].nblocks = grid;
+            blk.hctx[t].smem = smem;
+            blk.hctx[t].blk = &blk;
+        }
+        g_emu_block = &blk;
+        bool any = true;
+        while (any) {
+            any = false;
+            for (int t = 0; t < T; ++t) {
+                if (blk.done[t]) continue;
+                blk.current = t;
+                swapcontext(&blk.main_ctx, &blk.ctxs[t]);
+                if (!blk.done[t]) any = true;
+            }
+        }
+    }
+    free(smem);
+    for (int t = 0; t < T; ++t) free(blk.stacks[t]);
+    return cudaSuccess;
+}
+
+}  // namespace swiftly

@@ -1,0 +1,117 @@
+"""
+Kernel index algebra without a GPU: the CUDA kernel bodies (csrc/*.cuh) are
+compiled for the host with every CUDA thread running as a fibre
+(tests/emu/emu_runtime.h) and driven through the same C ABI and the same Python
+wrapper as the product.  TEST TOOLING ONLY -- the product never loads the
+emulated library; the real parity gate is tests/test_gpu_*.py on the B200.
+"""
+
+import ctypes
+import os
+import sys
+
+import numpy
+import pytest
+
+from tests import parity_cases as pc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu_core_cls():
+    sys.path.insert(0, os.path.join(HERE, "emu"))
+    import build_emu  # pylint: disable=import-error,import-outside-toplevel
+
+    path = build_emu.build()
+    from ska_sdp_distributed_fourier_transform_b200 import _lib, core
+
+    lib = _lib.load(path)
+    assert b"EMULATED" in lib.swiftly_b200_build_info()
+
+    class EmuCore(core.SwiftlyCoreB200):
+        """SwiftlyCoreB200 bound to the emulated library (tests only)."""
+
+        def __init__(self, W, N, xM_size, yN_size, force_split=False):
+            real_load = _lib.load
+            _lib.load = lambda path=None: lib
+            try:
+                super().__init__(W, N, xM_size, yN_size, device=0)
+            finally:
+                _lib.load = real_load
+            if force_split:
+                lib.swiftly_b200_debug_force_split.argtypes = [ctypes.c_void_p, ctypes.c_int]
+                lib.swiftly_b200_debug_force_split(self._plan, 1)
+
+    return EmuCore
+
+
+SMALL = dict(W=13.5625, N=256, xM=64, yN=128)     # m = 32
+TESTP = dict(W=13.5625, N=1024, xM=256, yN=512)   # m = 128 (reference TEST_PARAMS)
+MID = dict(W=13.5625, N=4096, xM=1024, yN=2048)   # m = 512: radix 16,16,8 / 16,16,4 / 16,16,2
+
+
+@pytest.mark.parametrize("p,yB,xA", [(SMALL, 96, 52), (SMALL, 95, 51), (TESTP, 416, 228),
+                                     (TESTP, 415, 227), (MID, 1500, 700)])
+def test_emu_1d_chain(emu_core_cls, p, yB, xA):
+    core, oracle = pc.make_pair(emu_core_cls, **p)
+    rng = numpy.random.default_rng(7)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    for f_off, s_off in [(0, 0), (3 * Ny, 5 * Nx), (-7 * Ny, -2 * Nx), (p["N"], p["N"] + Nx)]:
+        pc.check_1d_chain(core, oracle, yB, xA, f_off, s_off, rng)
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+def test_emu_2d_axes(emu_core_cls, axis):
+    core, oracle = pc.make_pair(emu_core_cls, **SMALL)
+    rng = numpy.random.default_rng(8)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    pc.check_2d_axis(core, oracle, 95, axis, 19, 5 * Ny, -3 * Nx, rng)
+    pc.check_2d_axis(core, oracle, 96, axis, 37, -Ny, 4 * Nx, rng)
+
+
+def test_emu_2d_subgrid_ops(emu_core_cls):
+    core, oracle = pc.make_pair(emu_core_cls, **SMALL)
+    rng = numpy.random.default_rng(9)
+    Nx = core.subgrid_off_step
+    pc.check_2d_subgrid_ops(core, oracle, 51, (2 * Nx, -Nx), rng)
+    pc.check_2d_subgrid_ops(core, oracle, 52, (0, 7 * Nx), rng)
+
+
+def test_emu_split_path(emu_core_cls):
+    """yN lines done as 2 x yN/2 (the path yN = 16384 takes on the GPU)."""
+    for p, yB in ((SMALL, 63), (TESTP, 250), (TESTP, 416)):
+        core, oracle = pc.make_pair(emu_core_cls, force_split=True, **p)
+        rng = numpy.random.default_rng(10)
+        Ny = core.facet_off_step
+        for f_off in (0, 3 * Ny, -9 * Ny):
+            facet = pc.rand_c(rng, 5, yB)
+            pc.close(core.prepare_facet(facet, f_off, axis=1),
+                     oracle.prepare_facet(facet, f_off, axis=1), what="split prepare_facet")
+            acc = pc.rand_c(rng, 5, p["yN"])
+            pc.close(core.finish_facet(acc, f_off, yB, axis=1),
+                     oracle.finish_facet(acc, f_off, yB, axis=1), what="split finish_facet")
+
+
+def test_emu_errors(emu_core_cls):
+    core, _ = pc.make_pair(emu_core_cls, **SMALL)
+    pc.check_errors(core)
+    with pytest.raises(ValueError):
+        emu_core_cls(13.5625, 1050, 256, 512)
+
+
+def test_emu_golden_1d(emu_core_cls, golden_1d):
+    g = golden_1d
+    core, _ = pc.make_pair(emu_core_cls, **TESTP)
+    for idx, (yB, xA, f_off, s_off) in enumerate(g["cases"][::5]):
+        idx = idx * 5
+        yB, xA, f_off, s_off = int(yB), int(xA), int(f_off), int(s_off)
+        k = lambda name: g[f"c{idx}_{name}"]  # noqa: E731
+        pc.close(core.prepare_facet(k("facet"), f_off, axis=0), k("prep"))
+        assert numpy.array_equal(core.extract_from_facet(k("prep"), s_off, axis=0), k("contrib"))
+        pc.close(core.add_to_subgrid(k("contrib"), f_off, axis=0), k("acc"))
+        pc.close(core.finish_subgrid(k("acc"), s_off, xA), k("sg"))
+        pc.close(core.prepare_subgrid(k("subgrid"), s_off), k("psg"))
+        pc.close(core.extract_from_subgrid(k("psg"), f_off, axis=0), k("ext"))
+        assert numpy.array_equal(core.add_to_facet(k("ext"), s_off, axis=0), k("accf"))
+        pc.close(core.finish_facet(k("accf"), f_off, yB, axis=0), k("fin"))
