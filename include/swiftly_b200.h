@@ -111,6 +111,38 @@ int swiftly_b200_finish_facet(const swiftly_b200* plan, const swiftly_b200_lines
                               const swiftly_b200_lines* out, int64_t facet_off,
                               const double* mask, void* stream);
 
+/* ---- fused forward path (device memory only) ---------------------------------------- */
+/* The reference's `extract_column` task (api_helper.py:200-210) in one kernel:
+ * extract_from_facet(BF_F, subgrid_off0, axis=0) followed by prepare_facet(., facet_off1,
+ * axis=1).  bf_f: yN_size lines (rows of the axis-0 prepared facet) of facet_size samples;
+ * out: xM_yN_size lines of yN_size samples (overwritten). */
+int swiftly_b200_extract_column(const swiftly_b200* plan, const swiftly_b200_lines* bf_f,
+                                const swiftly_b200_lines* out, int64_t subgrid_off0,
+                                int64_t facet_off1, void* stream);
+
+/* One input of swiftly_b200_sum_finish_axis: `n_lines` lines (n_lines of the output) of
+ * `size` samples.  size == yN_size: lines of a prepared facet, the contribution window for
+ * `subgrid_off` is extracted on the fly (extract_from_facet, core.py:224-253);
+ * size == xM_yN_size: lines that already are contributions. */
+typedef struct swiftly_b200_source {
+    const void* data; /* device pointer */
+    int64_t line_stride;
+    int64_t elem_stride;
+    int64_t size;
+    int64_t facet_off; /* facet offset along the transformed axis */
+} swiftly_b200_source;
+
+/* One axis of the reference's `sum_and_finish_subgrid` task (api_helper.py:73-112) in one
+ * kernel: for every line, sum_g add_to_subgrid(extract(source_g), facet_off_g) is built in
+ * shared memory and finished (finish_subgrid along this axis, mask folded in).  out:
+ * n_lines x subgrid_size (overwritten).  Returns SWIFTLY_B200_EUNSUPPORTED when the
+ * (xM_yN_size, xM_size) pair has no fused instantiation (callers then use the primitives). */
+int swiftly_b200_sum_finish_axis(const swiftly_b200* plan, const swiftly_b200_source* sources,
+                                 int n_sources, const swiftly_b200_lines* out,
+                                 int64_t subgrid_off, const double* mask, void* stream);
+/* xM_size / xM_yN_size if the fused kernel exists for this plan, else 0. */
+int swiftly_b200_sum_finish_axis_supported(const swiftly_b200* plan);
+
 #ifdef __cplusplus
 }
 #endif

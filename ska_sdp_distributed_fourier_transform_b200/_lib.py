@@ -36,6 +36,18 @@ class Lines(ctypes.Structure):
     ]
 
 
+class Source(ctypes.Structure):
+    """``swiftly_b200_source``: one input of the fused sum-and-finish kernel."""
+
+    _fields_ = [
+        ("data", ctypes.c_void_p),
+        ("line_stride", ctypes.c_int64),
+        ("elem_stride", ctypes.c_int64),
+        ("size", ctypes.c_int64),
+        ("facet_off", ctypes.c_int64),
+    ]
+
+
 _PLAN = ctypes.c_void_p
 _LINES_P = ctypes.POINTER(Lines)
 _D_P = ctypes.POINTER(ctypes.c_double)
@@ -59,6 +71,9 @@ SYMBOLS = {
     "swiftly_b200_extract_from_subgrid": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_add_to_facet": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_finish_facet": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "swiftly_b200_extract_column": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "swiftly_b200_sum_finish_axis": (ctypes.c_int, [_PLAN, ctypes.POINTER(Source), ctypes.c_int, _LINES_P, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "swiftly_b200_sum_finish_axis_supported": (ctypes.c_int, [_PLAN]),
 }
 
 _lock = threading.Lock()

@@ -165,9 +165,20 @@ class SwiftlyCoreB200:
 
     @staticmethod
     def _stream(a):
-        if _is_tensor(a):
+        if _is_tensor(a) and a.is_cuda:
             return ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
         return ctypes.c_void_p(0)
+
+    def _check_tensor(self, t):
+        """Device tensors must be complex128 on this plan's CUDA device."""
+        if not t.is_cuda:
+            raise ValueError(
+                "tensors must live on a CUDA device (use numpy arrays for host data)"
+            )
+        if t.device.index != self.device:
+            raise ValueError(
+                f"tensor is on cuda:{t.device.index}, the plan on cuda:{self.device}"
+            )
 
     def _mask_ptr(self, mask, like, keep):
         """Pointer to a float64 mask living where ``like`` lives (or NULL)."""
@@ -220,8 +231,9 @@ class SwiftlyCoreB200:
                     raise ValueError("output tensor must be complex128")
             elif out.dtype != numpy.complex128:
                 raise ValueError("output array must be complex128")
-        if _is_tensor(in_arr) and not in_arr.is_cuda:
-            raise ValueError("tensors must live on a CUDA device (use numpy arrays for host data)")
+        if _is_tensor(in_arr):
+            self._check_tensor(in_arr)
+            self._check_tensor(out)
         din = self._describe(in_arr, axis)
         dout = self._describe(out, axis)
         keep = []
@@ -323,3 +335,71 @@ class SwiftlyCoreB200:
         return self._run(
             "swiftly_b200_finish_facet", MiNjSi_sum, facet_size, axis, out, facet_off, mask=mask
         )
+
+    # ------------------------------------------------------------------ fused forward path
+    def fused_forward_supported(self):
+        """True if the fused subgrid kernels exist for this (xM_yN_size, xM_size) pair."""
+        return self._lib.swiftly_b200_sum_finish_axis_supported(self._plan) > 0
+
+    def extract_column(self, BF_F, subgrid_off0, facet_off1, out=None):
+        """``extract_column`` task of the reference (api_helper.py:200-210) as ONE kernel.
+
+        ``extract_from_facet(BF_F, subgrid_off0, axis=0)`` then
+        ``prepare_facet(., facet_off1, axis=1)``; device tensors only.
+        ``BF_F``: ``(yN_size, facet_size)``; result ``(xM_yN_size, yN_size)``.
+        """
+        if not _is_tensor(BF_F) or BF_F.dtype != torch.complex128 or BF_F.dim() != 2:
+            raise ValueError("extract_column needs a 2-D complex128 device tensor")
+        self._check_tensor(BF_F)
+        shape = (self.xM_yN_size, self.yN_size)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.complex128, device=BF_F.device)
+        elif tuple(out.shape) != shape:
+            raise ValueError(f"Output array has shape {tuple(out.shape)}, expected {shape}!")
+        din = self._describe(BF_F, 1)
+        dout = self._describe(out, 1)
+        rc = self._lib.swiftly_b200_extract_column(
+            self._plan, ctypes.byref(din), ctypes.byref(dout), int(subgrid_off0),
+            int(facet_off1), self._stream(BF_F),
+        )
+        _lib.check(self._lib, rc)
+        return out
+
+    def sum_finish_axis(self, sources, out, axis, subgrid_off, mask=None):
+        """One axis of ``sum_and_finish_subgrid`` (api_helper.py:73-112) as ONE kernel.
+
+        :param sources: list of ``(tensor, facet_off)``; every tensor is 2-D with the
+            transformed ``axis`` of length ``yN_size`` (prepared facet lines: the
+            contribution window for ``subgrid_off`` is cut on the fly) or
+            ``xM_yN_size`` (already contributions)
+        :param out: 2-D device tensor, ``axis`` of length subgrid size (overwritten)
+        :param mask: optional float64 device tensor of length subgrid size
+        """
+        if axis not in (0, 1):
+            raise ValueError(f"Invalid axis {axis}")
+        self._check_tensor(out)
+        arr = (_lib.Source * len(sources))()
+        other = 1 - axis
+        for i, (t, facet_off) in enumerate(sources):
+            self._check_tensor(t)
+            if t.dtype != torch.complex128 or t.dim() != 2:
+                raise ValueError("sources must be 2-D complex128 device tensors")
+            if t.shape[other] != out.shape[other]:
+                raise ValueError(
+                    f"source has {t.shape[other]} lines, output {out.shape[other]}"
+                )
+            arr[i] = _lib.Source(t.data_ptr(), t.stride(other), t.stride(axis), t.shape[axis],
+                                 int(facet_off))
+        dout = self._describe(out, axis)
+        mptr = ctypes.c_void_p(0)
+        if mask is not None:
+            if mask.dtype != torch.float64 or mask.numel() != out.shape[axis]:
+                raise ValueError("mask must be float64 of the subgrid size")
+            mask = mask.contiguous()
+            mptr = ctypes.c_void_p(mask.data_ptr())
+        rc = self._lib.swiftly_b200_sum_finish_axis(
+            self._plan, arr, len(sources), ctypes.byref(dout), int(subgrid_off), mptr,
+            self._stream(out),
+        )
+        _lib.check(self._lib, rc)
+        return out

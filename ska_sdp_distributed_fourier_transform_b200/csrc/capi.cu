@@ -6,7 +6,7 @@
 #include <string>
 #include <vector>
 
-#include "plan.h"
+#include "capi_util.h"
 
 using namespace swiftly;
 
@@ -50,17 +50,6 @@ const cplx* twiddles(const swiftly_b200* h, int n) {
 }
 
 }  // namespace swiftly
-
-static int einval(const std::string& msg) {
-    set_error(msg);
-    return SWIFTLY_B200_EINVAL;
-}
-
-#define SW_CUDA(call, what)                            \
-    do {                                               \
-        cudaError_t e__ = (call);                      \
-        if (e__ != cudaSuccess) return cuda_fail(e__, what); \
-    } while (0)
 
 // ------------------------------------------------------------------ plan
 extern "C" const char* swiftly_b200_last_error(void) { return g_last_error.c_str(); }
@@ -263,19 +252,7 @@ bool lines_adjacent(const Lines& g) {
     return g.n_lines > 1 && (g.in_ls == 1 || g.out_ls == 1) && g.in_es != 1;
 }
 
-inline int64_t floordiv(int64_t a, int64_t b) {  // python // for b > 0
-    int64_t q = a / b;
-    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
-    return q;
-}
-
 }  // namespace
-
-#define SW_TRY(expr)                         \
-    do {                                     \
-        int rc__ = (expr);                   \
-        if (rc__ != SWIFTLY_B200_OK) return rc__; \
-    } while (0)
 
 #define SW_PROLOGUE(what, in_size, out_size, copy_out)                          \
     if (!h) return einval(what ": NULL plan");                                  \

@@ -1,0 +1,134 @@
+// SwiFTly B200 -- C ABI of the fused forward-path entry points (device memory only).
+#include <vector>
+
+#include "capi_util.h"
+
+using namespace swiftly;
+
+// Fused extract_from_facet(axis 0) + prepare_facet(axis 1): the reference's
+// `extract_column` task (api_helper.py:200-210).
+extern "C" int swiftly_b200_extract_column(const swiftly_b200* h, const swiftly_b200_lines* bf_f,
+                                           const swiftly_b200_lines* out, int64_t subgrid_off0,
+                                           int64_t facet_off1, void* stream) {
+    if (!h || !bf_f || !out) return einval("extract_column: NULL argument");
+    if (bf_f->location != SWIFTLY_B200_DEVICE || out->location != SWIFTLY_B200_DEVICE)
+        return einval("extract_column: device arrays only");
+    const int64_t yN = h->yN, m = h->m, fs = bf_f->size;
+    if (bf_f->n_lines != yN)
+        return einval("extract_column: prepared facet must have yN_size lines, has " +
+                      std::to_string(bf_f->n_lines));
+    if (out->n_lines != m || out->size != yN)
+        return einval("extract_column: output must be xM_yN_size lines of yN_size samples");
+    if (fs > yN - 1) return einval("extract_column: facet size must be at most yN_size - 1");
+    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    const int64_t sc = floordiv(subgrid_off0 * yN, h->N);
+    PrepareFacetOp op;
+    op.g.in = (const cplx*)bf_f->data;
+    op.g.out = (cplx*)out->data;
+    op.g.in_ls = bf_f->line_stride;
+    op.g.in_es = bf_f->elem_stride;
+    op.g.out_ls = out->line_stride;
+    op.g.out_es = out->elem_stride;
+    op.g.n_lines = m;
+    op.n = (int)yN;
+    op.fs = (int)fs;
+    op.fb = h->d_Fb + ((yN - 1) / 2 - fs / 2);
+    op.shift_in = (int)pmod(fs / 2 - facet_off1, yN);
+    op.scale = 1.0 / (double)yN;
+    op.rm_m = (int)m;
+    op.rm_s_m = (int)pmod(sc, m);
+    op.rm_base = (int)pmod(yN / 2 - m / 2 + sc, yN);
+    op.rm_mod = (int)yN;
+    return run_prepare_facet(h, op, false, (cudaStream_t)stream);
+}
+
+extern "C" int swiftly_b200_sum_finish_axis_supported(const swiftly_b200* h) {
+    return h ? subgrid_axis_conc((int)h->m, (int)h->xM) : 0;
+}
+
+// Fused extract_from_facet + add_to_subgrid (summed over sources) + finish_subgrid along
+// one axis (SubgridAxisKernel, kernels.cuh).
+extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,
+                                            const swiftly_b200_source* sources, int n_sources,
+                                            const swiftly_b200_lines* out, int64_t subgrid_off,
+                                            const double* mask, void* stream) {
+    if (!h || !sources || !out) return einval("sum_finish_axis: NULL argument");
+    if (out->location != SWIFTLY_B200_DEVICE) return einval("sum_finish_axis: device arrays only");
+    const int64_t yN = h->yN, xM = h->xM, m = h->m;
+    const int conc = subgrid_axis_conc((int)m, (int)xM);
+    if (!conc) {
+        set_error("sum_finish_axis: no fused kernel for m=" + std::to_string(m) +
+                  ", xM=" + std::to_string(xM));
+        return SWIFTLY_B200_EUNSUPPORTED;
+    }
+    if (n_sources < 0) return einval("sum_finish_axis: negative source count");
+    const int64_t sz = out->size;
+    if (sz > xM) return einval("sum_finish_axis: subgrid size exceeds padded subgrid size");
+    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+
+    // schedule sources into rounds of `conc` with pairwise disjoint accumulator windows
+    struct Win { int pos; };
+    std::vector<std::vector<int>> rounds;
+    std::vector<int> pos_of((size_t)n_sources);
+    for (int i = 0; i < n_sources; ++i) {
+        const swiftly_b200_source& sr = sources[i];
+        if (!sr.data) return einval("sum_finish_axis: NULL source pointer");
+        if (sr.size != yN && sr.size != m)
+            return einval("sum_finish_axis: source line length must be yN_size or xM_yN_size");
+        const int64_t sf = floordiv(sr.facet_off * xM, h->N);
+        pos_of[i] = (int)pmod(xM / 2 - m / 2 + sf, xM);
+        bool placed = false;
+        for (auto& r : rounds) {
+            if ((int)r.size() >= conc) continue;
+            bool clash = false;
+            for (int j : r) {
+                int64_t d1 = pmod(pos_of[j] - pos_of[i], xM), d2 = pmod(pos_of[i] - pos_of[j], xM);
+                if (d1 < m || d2 < m) { clash = true; break; }
+            }
+            if (!clash) { r.push_back(i); placed = true; break; }
+        }
+        if (!placed) rounds.push_back(std::vector<int>(1, i));
+    }
+    if ((int)rounds.size() * conc > SW_MAX_SOURCES)
+        return einval("sum_finish_axis: too many sources for one launch (" +
+                      std::to_string(n_sources) + ")");
+    SubgridAxisArgs a;
+    for (int i = 0; i < SW_MAX_SOURCES; ++i) {
+        a.src[i].base = nullptr;
+        a.src[i].ls = a.src[i].es = 0;
+        a.src[i].wbase = a.src[i].s_m = a.src[i].sf_m = a.src[i].pos_base = 0;
+        a.src[i].wmod = 1;
+    }
+    const int64_t sc = floordiv(subgrid_off * yN, h->N);
+    for (size_t r = 0; r < rounds.size(); ++r) {
+        for (size_t c = 0; c < rounds[r].size(); ++c) {
+            const int i = rounds[r][c];
+            const swiftly_b200_source& sr = sources[i];
+            SgSource& d = a.src[r * conc + c];
+            d.base = (const cplx*)sr.data;
+            d.ls = sr.line_stride;
+            d.es = sr.elem_stride;
+            if (sr.size == yN && yN != m) {  // window of a prepared facet line
+                d.wbase = (int)pmod(yN / 2 - m / 2 + sc, yN);
+                d.s_m = (int)pmod(sc, m);
+                d.wmod = (int)yN;
+            } else {  // already a contribution
+                d.wbase = 0;
+                d.s_m = 0;
+                d.wmod = (int)m;
+            }
+            const int64_t sf = floordiv(sr.facet_off * xM, h->N);
+            d.sf_m = (int)pmod(sf, m);
+            d.pos_base = pos_of[i];
+        }
+    }
+    a.n_slots = (int)rounds.size() * conc;
+    a.n_lines = out->n_lines;
+    a.out = (cplx*)out->data;
+    a.out_ls = out->line_stride;
+    a.out_es = out->elem_stride;
+    a.sz = (int)sz;
+    a.start = (int)pmod(xM / 2 - sz / 2 + subgrid_off, xM);
+    a.mask = mask;
+    return run_subgrid_axis(h, a, (cudaStream_t)stream);
+}

@@ -44,10 +44,15 @@ struct PrepareFacetOp {
     int fs;            // facet size along the axis
     int shift_in;      // k = (q' + shift_in) mod n  with shift_in = (fs//2 - facet_off) mod n
     double scale;      // 1 / yN
+    // optional input row map (fused extract_from_facet along the OTHER axis,
+    // api_helper.py:200-210): input line = (rm_base + ((line - rm_s_m) mod rm_m)) mod rm_mod
+    int rm_m, rm_s_m, rm_base, rm_mod;
     SW_HD cplx load(int64_t line, int q) const {
         int k = wrap_add(q, shift_in, n);
         if (k >= fs) return mk(0.0, 0.0);
-        return cscale(ldg_c(g.in + line * g.in_ls + (int64_t)k * g.in_es), ldg_d(fb + k));
+        int64_t row = rm_m ? (int64_t)wrap_add(rm_base, wrap_sub((int)line, rm_s_m, rm_m), rm_mod)
+                           : line;
+        return cscale(ldg_c(g.in + row * g.in_ls + (int64_t)k * g.in_es), ldg_d(fb + k));
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, n / 2, n);
@@ -271,6 +276,110 @@ struct WindowCopyKernel {
                 g.out[line * g.out_ls + (int64_t)t * g.out_es] =
                     ldg_c(g.in + line * g.in_ls + (int64_t)w * g.in_es);
             }
+        }
+    }
+};
+
+
+// ------------------------------------------------------------------ fused subgrid axis kernel
+// One axis of "sum the contributions of several sources and finish":
+//   for every output line l:
+//     acc[0..xM) = 0
+//     for every source g:  c = window of source line l   (extract_from_facet, core.py:224-253)
+//                          acc[(pos_g + u) mod xM] += Fn[u] * fft_c(c)[(u + sf_g) mod m]
+//                                                           (add_to_subgrid, core.py:255-285)
+//     out[l, r] = mask[r] * ifft_c(acc)[(start + r) mod xM], r < sz
+//                                                           (finish_subgrid, core.py:287-325)
+// The padded accumulator lives in shared memory only: neither the (m) contributions nor the
+// (xM) accumulators of the reference's sum_and_finish_subgrid (api_helper.py:73-112) ever
+// touch HBM.  Used twice per subgrid: along axis 1 with the facets of one facet row as
+// sources (windows of their NMBF_BF buffers), then along axis 0 with the per-row strips as
+// sources.  Sources are processed CONC = xM/m at a time ("rounds"); the host orders them so
+// that the windows inside one round do not overlap (plain read-modify-write on acc).
+struct SgSource {
+    const cplx* base;      // nullptr: empty slot
+    int64_t ls, es;        // stride between task lines / between samples (complex elements)
+    int wbase, s_m, wmod;  // sample index of centred contribution index tc:
+                           //   (wbase + ((tc - s_m) mod m)) mod wmod
+    int sf_m, pos_base;    // sf mod m ; (xM/2 - m/2 + sf) mod xM
+};
+#define SW_MAX_SOURCES 64
+
+template <int M, int XM>
+struct SubgridAxisKernel {
+    static constexpr int T_M = FftCfg<M>::T;
+    static constexpr int THREADS = FftCfg<XM>::T;
+    static constexpr int CONC = THREADS / T_M;  // = XM / M concurrent m-point transforms
+    static constexpr int WSTRIDE = FftCfg<M>::PADDED | 1;
+    static constexpr int WORK = CONC * WSTRIDE;  // >= FftCfg<XM>::PADDED
+    static_assert(WORK >= FftCfg<XM>::PADDED, "work area must hold the xM exchange buffer");
+    static constexpr size_t SMEM = (size_t)(XM + WORK) * sizeof(cplx);
+
+    SgSource src[SW_MAX_SOURCES];
+    int n_slots;
+    const double* fn;
+    const cplx* tw_m;
+    const cplx* tw_x;
+    int64_t n_lines;
+    cplx* out;
+    int64_t out_ls, out_es;
+    int sz, start;
+    double scale;        // 1 / xM
+    const double* mask;  // sz doubles or null
+
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        cplx* acc = (cplx*)ctx.smem;
+        cplx* work = acc + XM;
+        const int c = ctx.tid / T_M;
+        const int lt = ctx.tid % T_M;
+        auto sync = [&]() { ctx.sync(); };
+        for (int64_t line = ctx.bid; line < n_lines; line += ctx.nblocks) {
+            for (int i = ctx.tid; i < XM; i += THREADS) acc[i] = mk(0.0, 0.0);
+            ctx.sync();
+            for (int slot0 = 0; slot0 < n_slots; slot0 += CONC) {
+                const int slot = slot0 + c;
+                const bool active = slot < n_slots && src[slot].base != nullptr;
+                // keep the descriptor in registers (kernel parameters live in constant memory)
+                const cplx* base = active ? src[slot].base + line * src[slot].ls : nullptr;
+                const int64_t es = active ? src[slot].es : 0;
+                const int wbase = active ? src[slot].wbase : 0;
+                const int s_m = active ? src[slot].s_m : 0;
+                const int wmod = active ? src[slot].wmod : 1;
+                const int sf_m = active ? src[slot].sf_m : 0;
+                const int pos_base = active ? src[slot].pos_base : 0;
+                auto ld = [&](int t) {
+                    if (!active) return mk(0.0, 0.0);
+                    int tc = wrap_add(t, M / 2, M);
+                    int idx = wrap_add(wbase, wrap_sub(tc, s_m, M), wmod);
+                    return ldg_c(base + (int64_t)idx * es);
+                };
+                auto st = [&](int w, cplx v) {
+                    if (!active) return;
+                    int wc = wrap_add(w, M / 2, M);
+                    int u = wrap_sub(wc, sf_m, M);
+                    int pos = wrap_add(pos_base, u, XM);
+                    double f = ldg_d(fn + u);
+                    cplx a = acc[pos];
+                    acc[pos] = mk(a.x + f * v.x, a.y + f * v.y);
+                };
+                line_fft<M, -1>(lt, work + (size_t)c * WSTRIDE, tw_m, ld, st, sync);
+                ctx.sync();
+            }
+            {
+                cplx* o = out + line * out_ls;
+                auto ld = [&](int q) { return acc[wrap_add(q, XM / 2, XM)]; };
+                auto st = [&](int p, cplx v) {
+                    int pc = wrap_add(p, XM / 2, XM);
+                    int r = wrap_sub(pc, start, XM);
+                    if (r < sz) {
+                        double f = mask ? scale * ldg_d(mask + r) : scale;
+                        o[(int64_t)r * out_es] = cscale(v, f);
+                    }
+                };
+                line_fft<XM, +1>(ctx.tid, work, tw_x, ld, st, sync);
+            }
+            ctx.sync();  // acc / work are reused by the next line
         }
     }
 };

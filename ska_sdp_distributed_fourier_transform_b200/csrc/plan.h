@@ -43,4 +43,19 @@ int run_extract_from_subgrid(const swiftly_b200* h, const ExtractFromSubgridOp& 
 int run_finish_subgrid(const swiftly_b200* h, const FinishSubgridOp& op, bool line_fastest, cudaStream_t s);
 int run_prepare_subgrid(const swiftly_b200* h, const PrepareSubgridOp& op, bool line_fastest, cudaStream_t s);
 
+// fused subgrid axis kernel (dispatch_subgrid_axis.cu); `k` carries everything but the tables
+struct SubgridAxisArgs {
+    SgSource src[SW_MAX_SOURCES];
+    int n_slots;
+    int64_t n_lines;
+    cplx* out;
+    int64_t out_ls, out_es;
+    int sz, start;
+    const double* mask;
+};
+// returns SWIFTLY_B200_EUNSUPPORTED (without setting up anything) when the (m, xM) pair has no
+// fused instantiation; conc_out receives the number of sources processed concurrently
+int subgrid_axis_conc(int m, int xM);
+int run_subgrid_axis(const swiftly_b200* h, const SubgridAxisArgs& a, cudaStream_t s);
+
 }  // namespace swiftly

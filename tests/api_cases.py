@@ -1,0 +1,134 @@
+"""
+Shared API-level checks (SwiftlyForward / SwiftlyBackward / fused kernels) run by
+tests/test_gpu_api.py on the B200 and by tests/test_emu_api.py on the host-emulated
+kernels.  ``make_config(W, N, yB, yN, xA, xM)`` returns a SwiftlyConfig.
+"""
+
+import numpy
+import torch
+
+from oracle.swiftly_oracle import OracleCore, forward_reference_order
+from ska_sdp_distributed_fourier_transform_b200 import (
+    FacetConfig,
+    SwiftlyBackward,
+    SwiftlyForward,
+    check_facet,
+    check_subgrid,
+    make_facet,
+    make_full_facet_cover,
+    make_full_subgrid_cover,
+)
+from ska_sdp_distributed_fourier_transform_b200.api import _device_of
+from tests import parity_cases as pc
+
+
+def devof(cfg):
+    return _device_of(cfg.core)
+
+
+def dev(cfg, arr):
+    return torch.from_numpy(numpy.ascontiguousarray(arr)).to(devof(cfg))
+
+
+def case_fused_ops_vs_oracle(make_config):
+    cfg = make_config(13.5625, 256, 96, 128, 52, 64)
+    core = cfg.core
+    oracle = OracleCore(13.5625, 256, 64, 128)
+    assert core.fused_forward_supported()
+    rng = numpy.random.default_rng(3)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    bf = pc.rand_c(rng, 128, 95)
+    got = core.extract_column(dev(cfg, bf), 7 * Nx, -5 * Ny).cpu().numpy()
+    ref = oracle.prepare_facet(oracle.extract_from_facet(bf, 7 * Nx, axis=0), -5 * Ny, axis=1)
+    pc.close(got, ref, what="extract_column")
+    # sum_finish along axis 1: three prepared-facet sources with overlapping windows
+    srcs = [pc.rand_c(rng, 32, 128) for _ in range(3)]
+    offs = [0, 24 * Ny, -24 * Ny]
+    mask = (rng.random(51) > 0.3).astype(float)
+    out = torch.empty((32, 51), dtype=torch.complex128, device=devof(cfg))
+    core.sum_finish_axis([(dev(cfg, s), o) for s, o in zip(srcs, offs)], out, axis=1,
+                         subgrid_off=-3 * Nx, mask=dev(cfg, mask))
+    acc = None
+    for s, o in zip(srcs, offs):
+        acc = oracle.add_to_subgrid(oracle.extract_from_facet(s, -3 * Nx, axis=1), o, axis=1, out=acc)
+    # finish along axis 1 only: use the 1-D finish on every row
+    ref = numpy.array([oracle.finish_subgrid(row, -3 * Nx, 51) for row in acc]) * mask[None, :]
+    pc.close(out.cpu().numpy(), ref, what="sum_finish_axis axis1")
+    # axis 0 with contribution-sized sources (strips)
+    strips = [pc.rand_c(rng, 32, 40) for _ in range(2)]
+    out0 = torch.empty((52, 40), dtype=torch.complex128, device=devof(cfg))
+    core.sum_finish_axis([(dev(cfg, s), o) for s, o in zip(strips, [0, 24 * Ny])], out0,
+                         axis=0, subgrid_off=5 * Nx)
+    acc = None
+    for s, o in zip(strips, [0, 24 * Ny]):
+        acc = oracle.add_to_subgrid(s, o, axis=0, out=acc)
+    ref = numpy.array([oracle.finish_subgrid(col, 5 * Nx, 52) for col in acc.T]).T
+    pc.close(out0.cpu().numpy(), ref, what="sum_finish_axis axis0")
+
+
+def case_forward_backward_vs_reference_golden(make_config, golden_2d):
+    g = golden_2d
+    W, N, xM, yN, yB, xA = g["params"]
+    cfg = make_config(float(W), int(N), int(yB), int(yN), int(xA), int(xM))
+    facet_cfgs = make_full_facet_cover(cfg)
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    assert [(c.off0, c.off1) for c in facet_cfgs] == [tuple(o) for o in g["facet_offs"]]
+    assert [(c.off0, c.off1) for c in sg_cfgs] == [tuple(o) for o in g["sg_offs"]]
+    fwd = SwiftlyForward(cfg, list(zip(facet_cfgs, g["facets"])), lru_forward=1, queue_size=5)
+    bwd = SwiftlyBackward(cfg, facet_cfgs, lru_backward=1, queue_size=5)
+    scale = numpy.abs(g["subgrids"]).max()
+    for i, sg in enumerate(sg_cfgs):
+        task = fwd.get_subgrid_task(sg)
+        got = task.result()
+        assert numpy.abs(got - g["subgrids"][i]).max() <= 1e-12 * scale, f"subgrid {i}"
+        bwd.add_new_subgrid_task(sg, task)
+    facets = [t.result() for t in bwd.finish()]
+    bscale = numpy.abs(g["back_facets"]).max()
+    for got, ref in zip(facets, g["back_facets"]):
+        assert numpy.abs(got - ref).max() <= 1e-11 * bscale
+
+
+def case_sparse_facets_shuffled_subgrids(make_config):
+    """Arbitrary facet list (sparse cover, ragged rows) and shuffled subgrid order."""
+    W, N, yB, yN, xA, xM = 13.5625, 256, 96, 128, 52, 64
+    cfg = make_config(W, N, yB, yN, xA, xM)
+    oracle = OracleCore(W, N, xM, yN)
+    rng = numpy.random.default_rng(5)
+    offs = [(0, 0), (0, 96), (96, 0), (-96, 192), (192, 192)]
+    facet_cfgs = [FacetConfig(o0, o1, yB) for o0, o1 in offs]
+    facets = [pc.rand_c(rng, yB, yB) for _ in offs]
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    order = rng.permutation(len(sg_cfgs))[:7]
+    fwd = SwiftlyForward(cfg, list(zip(facet_cfgs, facets)), lru_forward=2, queue_size=3)
+    got = [fwd.get_subgrid_task(sg_cfgs[i]).result() for i in order]
+    ref = forward_reference_order(
+        oracle, facets, offs, [(sg_cfgs[i].off0, sg_cfgs[i].off1) for i in order], xA,
+        subgrid_masks=[(sg_cfgs[i].mask0, sg_cfgs[i].mask1) for i in order],
+    )
+    scale = max(numpy.abs(r).max() for r in ref)
+    for a, b in zip(got, ref):
+        assert numpy.abs(a - b).max() <= 1e-12 * scale
+
+
+def case_api_round_trip(make_config, lru_forward, lru_backward, shuffle):
+    """reference tests/test_api.py:56-125 (round trip, unit source, facet RMSE < 3e-10)."""
+    import random
+
+    p = dict(W=13.5625, N=1024, yB=416, yN=512, xA=228, xM=256)
+    cfg = make_config(**p)
+    sources = [(1, 1, 0)]
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    facet_cfgs = make_full_facet_cover(cfg)
+    facet_tasks = [(fc, make_facet(cfg.image_size, fc, sources)) for fc in facet_cfgs]
+    fwd = SwiftlyForward(cfg, facet_tasks, lru_forward, 100)
+    bwd = SwiftlyBackward(cfg, facet_cfgs, lru_backward, 100)
+    if shuffle:
+        random.Random(1).shuffle(sg_cfgs)
+    worst_sg = 0.0
+    for sg in sg_cfgs:
+        task = fwd.get_subgrid_task(sg)
+        worst_sg = max(worst_sg, check_subgrid(cfg.image_size, sg, task.tensor, sources))
+        bwd.add_new_subgrid_task(sg, task)
+    assert worst_sg < 1e-13
+    for fc, task in zip(facet_cfgs, bwd.finish()):
+        assert check_facet(cfg.image_size, fc, task.result(), sources) < 3e-10

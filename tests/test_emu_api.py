@@ -1,0 +1,34 @@
+"""
+SwiftlyForward / SwiftlyBackward host logic and fused-kernel index algebra on the
+host-emulated kernels (no GPU): compared with the reference-generated golden 2-D
+fixture and with the oracle.  TEST TOOLING -- see tests/test_emu_parity.py.
+"""
+
+import pytest
+
+from ska_sdp_distributed_fourier_transform_b200 import SwiftlyConfig
+from tests import api_cases
+from tests.emu_support import emu_core_class
+
+
+def make_config(W, N, yB, yN, xA, xM, **kw):
+    core = emu_core_class()(W, N, xM, yN, **kw)
+    return SwiftlyConfig(W=W, fov=1.0, N=N, yB_size=yB, yN_size=yN, xA_size=xA, xM_size=xM,
+                         core=core)
+
+
+def test_emu_fused_ops_vs_oracle():
+    api_cases.case_fused_ops_vs_oracle(make_config)
+
+
+def test_emu_forward_backward_vs_reference_golden(golden_2d):
+    api_cases.case_forward_backward_vs_reference_golden(make_config, golden_2d)
+
+
+def test_emu_sparse_facets_shuffled_subgrids():
+    api_cases.case_sparse_facets_shuffled_subgrids(make_config)
+
+
+@pytest.mark.parametrize("lru_forward,lru_backward,shuffle", [(1, 1, False), (2, 2, True)])
+def test_emu_api_round_trip(lru_forward, lru_backward, shuffle):
+    api_cases.case_api_round_trip(make_config, lru_forward, lru_backward, shuffle)

@@ -6,44 +6,17 @@ wrapper as the product.  TEST TOOLING ONLY -- the product never loads the
 emulated library; the real parity gate is tests/test_gpu_*.py on the B200.
 """
 
-import ctypes
-import os
-import sys
-
 import numpy
 import pytest
 
 from tests import parity_cases as pc
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-
 
 @pytest.fixture(scope="module")
 def emu_core_cls():
-    sys.path.insert(0, os.path.join(HERE, "emu"))
-    import build_emu  # pylint: disable=import-error,import-outside-toplevel
+    from tests.emu_support import emu_core_class
 
-    path = build_emu.build()
-    from ska_sdp_distributed_fourier_transform_b200 import _lib, core
-
-    lib = _lib.load(path)
-    assert b"EMULATED" in lib.swiftly_b200_build_info()
-
-    class EmuCore(core.SwiftlyCoreB200):
-        """SwiftlyCoreB200 bound to the emulated library (tests only)."""
-
-        def __init__(self, W, N, xM_size, yN_size, force_split=False):
-            real_load = _lib.load
-            _lib.load = lambda path=None: lib
-            try:
-                super().__init__(W, N, xM_size, yN_size, device=0)
-            finally:
-                _lib.load = real_load
-            if force_split:
-                lib.swiftly_b200_debug_force_split.argtypes = [ctypes.c_void_p, ctypes.c_int]
-                lib.swiftly_b200_debug_force_split(self._plan, 1)
-
-    return EmuCore
+    return emu_core_class()
 
 
 SMALL = dict(W=13.5625, N=256, xM=64, yN=128)     # m = 32

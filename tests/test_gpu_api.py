@@ -1,0 +1,77 @@
+"""
+GPU API parity: SwiftlyForward / SwiftlyBackward and the fused kernels on the B200
+against the reference-generated golden fixture, the oracle and the reference's
+round-trip criterion (tests/test_api.py:125, facet RMSE < 3e-10), plus the BASELINE
+cfg2 geometry (N=8192) checked stage by stage against the oracle and -- for point
+sources -- against the analytic DFT.
+"""
+
+import numpy
+import pytest
+import torch
+
+from oracle.swiftly_oracle import OracleCore, forward_reference_order
+from ska_sdp_distributed_fourier_transform_b200 import (
+    FacetConfig,
+    SubgridConfig,
+    SwiftlyConfig,
+    SwiftlyForward,
+    check_subgrid,
+    make_facet,
+    make_full_facet_cover,
+    make_full_subgrid_cover,
+)
+from tests import api_cases
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_config(W, N, yB, yN, xA, xM, **kw):
+    return SwiftlyConfig(W=W, fov=1.0, N=N, yB_size=yB, yN_size=yN, xA_size=xA, xM_size=xM)
+
+
+def test_fused_ops_vs_oracle():
+    api_cases.case_fused_ops_vs_oracle(make_config)
+
+
+def test_forward_backward_vs_reference_golden(golden_2d):
+    api_cases.case_forward_backward_vs_reference_golden(make_config, golden_2d)
+
+
+def test_sparse_facets_shuffled_subgrids():
+    api_cases.case_sparse_facets_shuffled_subgrids(make_config)
+
+
+@pytest.mark.parametrize(
+    "lru_forward,lru_backward,shuffle",
+    [(1, 1, False), (2, 1, False), (1, 2, False), (1, 1, True), (2, 1, True), (1, 2, True)],
+)
+def test_api_round_trip(lru_forward, lru_backward, shuffle):
+    api_cases.case_api_round_trip(make_config, lru_forward, lru_backward, shuffle)
+
+
+def test_cfg2_forward_vs_oracle_and_dft():
+    """BASELINE cfg2 (N=8192, m=1024, xM=2048): fused GPU pipeline vs the oracle on dense
+    random facets (two facets, three subgrids) and vs the analytic DFT for point sources."""
+    W, N, yB, yN, xA, xM = 13.5625, 8192, 2048, 4096, 1024, 2048
+    cfg = make_config(W, N, yB, yN, xA, xM)
+    oracle = OracleCore(W, N, xM, yN)
+    rng = numpy.random.default_rng(123456789)
+    offs = [(0, 0), (0, 2048)]
+    facets = [pc.rand_c(rng, yB, yB) for _ in offs]
+    sgs = [SubgridConfig(1024, 3072, xA), SubgridConfig(1024, 0, xA), SubgridConfig(-2048, 1024, xA)]
+    fwd = SwiftlyForward(cfg, [(FacetConfig(o0, o1, yB), f) for (o0, o1), f in zip(offs, facets)])
+    got = [fwd.get_subgrid_task(sg).result() for sg in sgs]
+    ref = forward_reference_order(oracle, facets, offs, [(s.off0, s.off1) for s in sgs], xA)
+    for a, b in zip(got, ref):
+        assert numpy.abs(a - b).max() <= 1e-11 * numpy.abs(b).max()
+    # point sources, full facet cover, a few subgrids: analytic truth
+    sources = [(float(rng.random()), int(rng.integers(-N // 2, N // 2)),
+                int(rng.integers(-N // 2, N // 2))) for _ in range(8)]
+    facet_cfgs = make_full_facet_cover(cfg)
+    fwd = SwiftlyForward(cfg, [(fc, make_facet(N, fc, sources)) for fc in facet_cfgs])
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    for sg in (sg_cfgs[0], sg_cfgs[9], sg_cfgs[-1]):
+        err = check_subgrid(N, sg, fwd.get_subgrid_task(sg).tensor, sources)
+        assert err < 1e-13, err

@@ -94,15 +94,21 @@ def test_device_tensor_mode(core_cls):
     osg = oracle.finish_subgrid(oacc, [s0, s1], 228)
     pc.close(acc.cpu().numpy(), oacc, what="device chain acc")
     pc.close(sg.cpu().numpy(), osg, rtol=1e-10, what="device chain subgrid")
-    # backward on device
+    # backward on device.  At yB/yN = 0.8125 the chain amplifies fp64 rounding by ~4e6
+    # (Fb reaches 4.9e3 per axis; a 1e-16 relative perturbation of the contribution moves
+    # the facet by 4e-10), so the strict chain check uses the well-conditioned yB = 256
+    # (the BASELINE geometries have yB/yN = 0.5) and the TEST_PARAMS round trip is judged
+    # by the reference's own criterion in tests/test_gpu_api.py.
+    yB = 256
     psg = core.prepare_subgrid(torch.from_numpy(osg).cuda(), (s0, s1))
     e = core.extract_from_subgrid(core.extract_from_subgrid(psg, f0, axis=0), f1, axis=1)
     a = core.add_to_facet(core.add_to_facet(e, s0, axis=0), s1, axis=1)
-    fin = core.finish_facet(core.finish_facet(a, f0, 416, axis=0), f1, 416, axis=1)
+    fin = core.finish_facet(core.finish_facet(a, f0, yB, axis=0), f1, yB, axis=1)
     opsg = oracle.prepare_subgrid(osg, (s0, s1))
     oe = oracle.extract_from_subgrid(oracle.extract_from_subgrid(opsg, f0, axis=0), f1, axis=1)
     oa = oracle.add_to_facet(oracle.add_to_facet(oe, s0, axis=0), s1, axis=1)
-    ofin = oracle.finish_facet(oracle.finish_facet(oa, f0, 416, axis=0), f1, 416, axis=1)
+    ofin = oracle.finish_facet(oracle.finish_facet(oa, f0, yB, axis=0), f1, yB, axis=1)
+    pc.close(e.cpu().numpy(), oe, rtol=1e-11, what="device backward contribution")
     pc.close(fin.cpu().numpy(), ofin, rtol=1e-10, what="device backward chain")
 
 
