@@ -294,6 +294,40 @@ def _to_device(data, device, dtype=None):
     return torch.from_numpy(numpy.ascontiguousarray(arr)).to(device, non_blocking=True)
 
 
+def _upload_iter(datas, device):
+    """Yield device tensors for ``datas`` in order.
+
+    Host sources are uploaded on a side stream one item ahead of the consumer, so that the
+    H2D copy of facet ``j + 1`` overlaps the kernels working on facet ``j`` (pinned host
+    memory makes the copy asynchronous; pageable memory still works, without overlap).
+    """
+    datas = list(datas)
+    use_side = device.type == "cuda"
+    side = torch.cuda.Stream(device) if use_side else None
+
+    def upload(data):
+        data = _resolve(data)
+        if isinstance(data, torch.Tensor) and data.device == device:
+            return _to_device(data, device), None
+        if not use_side:
+            return _to_device(data, device), None
+        with torch.cuda.stream(side):
+            t = _to_device(data, device)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return t, ev
+
+    nxt = upload(datas[0]) if datas else None
+    for j in range(len(datas)):
+        cur = nxt
+        nxt = upload(datas[j + 1]) if j + 1 < len(datas) else None
+        t, ev = cur
+        if ev is not None:
+            torch.cuda.current_stream(device).wait_event(ev)
+            t.record_stream(torch.cuda.current_stream(device))
+        yield t
+
+
 def _device_mask(mask, device):
     """float64 device mask, or None when the mask is absent or all ones."""
     if mask is None:
@@ -345,8 +379,8 @@ class SwiftlyForward:
     def _get_BF_Fs(self):
         if self.BF_Fs_persist is None:
             out = []
-            for idx, (cfg, data) in enumerate(self.facet_tasks):
-                facet = _to_device(_resolve(data), self.device)
+            uploads = _upload_iter([data for _, data in self.facet_tasks], self.device)
+            for idx, ((cfg, _), facet) in enumerate(zip(self.facet_tasks, uploads)):
                 buf = None if self._bf_f_buffers is None else self._bf_f_buffers[idx]
                 out.append(self.core.prepare_facet(facet, cfg.off0, axis=0, out=buf))
                 del facet

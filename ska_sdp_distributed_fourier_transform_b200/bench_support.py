@@ -1,0 +1,246 @@
+"""
+Benchmark driver for the forward transform (used by ``bench.py``).
+
+Keeps the measurement logic next to the API it measures: the timed region calls the
+public ``SwiftlyForward`` (one GPU) or ``SwiftlyForwardSharded`` (one rank per GPU)
+classes, nothing else.
+"""
+
+import time
+
+import numpy
+import torch
+import torch.distributed as dist
+
+from .api import (
+    SwiftlyConfig,
+    SwiftlyForward,
+    make_full_facet_cover,
+    make_full_subgrid_cover,
+)
+from .distributed import SwiftlyForwardSharded, partition_facets
+
+MIB = float(1 << 20)
+
+
+class ForwardBenchRunner:
+    """Synthetic full-cover forward transform of one parameter set on ``world`` GPUs."""
+
+    # pylint: disable=too-many-instance-attributes
+    def __init__(self, params, device, rank=0, world=1):
+        self.params = dict(params)
+        self.device = device
+        self.rank = rank
+        self.world = world
+        self.cfg = SwiftlyConfig(device=device.index, **params)
+        self.core = self.cfg.core
+        self.facet_cfgs = make_full_facet_cover(self.cfg)
+        self.sg_cfgs = make_full_subgrid_cover(self.cfg)
+        self.owner = partition_facets(self.facet_cfgs, world)
+        self.local_idx = [i for i, o in enumerate(self.owner) if o == rank]
+        self.yB = params["yB_size"]
+        self.yN = params["yN_size"]
+        self.xA = params["xA_size"]
+        self.xM = params["xM_size"]
+        self.m = self.core.xM_yN_size
+        F = len(self.local_idx)
+        u = self.yB * self.yB  # facet elements
+        b = self.yN * self.yB  # prepared facet elements
+        # One arena: BF_F[k] at k*b; facet[k] at F*(b-u) + u + k*u.  Stage 1 processes the
+        # facets in order; BF_F[k] never reaches a facet that is still unread,
+        # so 64 GiB of facets + 128 GiB of BF_F fit in 129 GiB on one GPU at cfg4.
+        self.arena = torch.empty(F * b + u, dtype=torch.complex128, device=device)
+        self.bf_views = {}
+        self.facet_views = {}
+        base = F * (b - u) + u
+        for k, idx in enumerate(self.local_idx):
+            self.bf_views[idx] = self.arena[k * b:(k + 1) * b].view(self.yN, self.yB)
+            self.facet_views[idx] = self.arena[base + k * u: base + (k + 1) * u].view(
+                self.yB, self.yB)
+        self.contributions_per_step = len(self.facet_cfgs) * len(self.sg_cfgs)
+        nrows = len({c.off0 for c in self.facet_cfgs})
+        ncols = len({s.off0 for s in self.sg_cfgs})
+        rows_local = len({self.facet_cfgs[i].off0 for i in self.local_idx})
+        # launches of OUR kernels per step on this rank (stage 1, stage 2, axis-1, axis-0)
+        owned_sg = len([i for i in range(len(self.sg_cfgs)) if i % world == rank])
+        self.launches_per_step = (F + ncols * F + len(self.sg_cfgs) * rows_local + owned_sg)
+        self._nrows = nrows
+        self._gen = torch.Generator(device=device)
+
+    # ------------------------------------------------------------------ data
+    def regenerate_facets(self):
+        """Dense standard-normal facets (seed 123456789 + facet index), on the device."""
+        for idx in self.local_idx:
+            self._gen.manual_seed(123456789 + idx)
+            torch.view_as_real(self.facet_views[idx]).normal_(generator=self._gen)
+
+    # ------------------------------------------------------------------ one step
+    def _run_forward(self, facet_data, consumer=None):
+        if self.world == 1:
+            fwd = SwiftlyForward(
+                self.cfg, [(fc, facet_data[i]) for i, fc in enumerate(self.facet_cfgs)],
+                lru_forward=1, queue_size=4,
+                bf_f_buffers=[self.bf_views[i] for i in range(len(self.facet_cfgs))])
+            for i, sg in enumerate(self.sg_cfgs):
+                task = fwd.get_subgrid_task(sg)
+                if consumer is not None:
+                    consumer(i, sg, task.tensor)
+            return
+        fwd = SwiftlyForwardSharded(self.cfg, self.facet_cfgs, facet_data, lru_forward=1,
+                                    bf_f_buffers=self.bf_views)
+        fwd.get_subgrid_tasks(self.sg_cfgs, consumer=consumer or (lambda *a: None))
+
+    def _barrier(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.device)
+
+    def step(self, timed=True):
+        """One complete forward transform; returns its time in ms (max over ranks)."""
+        self.regenerate_facets()
+        self._barrier()
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record()
+        self._run_forward(self.facet_views)
+        end.record()
+        self._barrier()
+        ms = start.elapsed_time(end)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms if timed else None
+
+    # ------------------------------------------------------------------ per-kernel rooflines
+    def _time(self, fn, reps=5):
+        fn()
+        torch.cuda.synchronize(self.device)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        evs[0].record()
+        for i in range(reps):
+            fn()
+            evs[i + 1].record()
+        torch.cuda.synchronize(self.device)
+        return float(numpy.mean([evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]))
+
+    def kernel_rooflines(self, hbm_gbs, step_ms=None):
+        """Average duration (CUDA events, this stream) of each kernel of the step, with its
+        algorithmic bytes and the HBM-roofline fraction."""
+        core, dev = self.core, self.device
+        yB, yN, xA, m = self.yB, self.yN, self.xA, self.m
+        fcs = self.facet_cfgs
+        idx0 = self.local_idx[0]
+        row_members = [i for i in self.local_idx if fcs[i].off0 == fcs[idx0].off0]
+        nsrc = len(row_members)
+        F = len(self.local_idx)
+        ncols = len({s.off0 for s in self.sg_cfgs})
+        S = len(self.sg_cfgs)
+        rows_local = len({fcs[i].off0 for i in self.local_idx})
+        owned_sg = len([i for i in range(S) if i % self.world == self.rank])
+        self.regenerate_facets()
+        sg = self.sg_cfgs[len(self.sg_cfgs) // 2 + 3]
+        out = {}
+        t1 = self._time(lambda: core.prepare_facet(
+            self.facet_views[idx0], fcs[idx0].off0, axis=0, out=self.bf_views[idx0]), 3)
+        out["prepare_facet_axis0"] = (t1, 16.0 * (yB * yB + yN * yB), F)
+        # make the row's BF_F valid for the following kernels
+        for i in row_members:
+            core.prepare_facet(self.facet_views[i], fcs[i].off0, axis=0, out=self.bf_views[i])
+        nmbf = {i: torch.empty((m, yN), dtype=torch.complex128, device=dev) for i in row_members}
+        t2 = self._time(lambda: core.extract_column(
+            self.bf_views[idx0], sg.off0, fcs[idx0].off1, out=nmbf[idx0]))
+        out["extract_column (Fb.FFT.extract, K2)"] = (t2, 16.0 * (m * yB + m * yN), ncols * F)
+        for i in row_members:
+            core.extract_column(self.bf_views[i], sg.off0, fcs[i].off1, out=nmbf[i])
+        nstrips = self._nrows
+        strips = torch.empty((nstrips, m, xA), dtype=torch.complex128, device=dev)
+        srcs = [(nmbf[i], fcs[i].off1) for i in row_members]
+        t3 = self._time(lambda: core.sum_finish_axis(srcs, strips[0], axis=1, subgrid_off=sg.off1))
+        out["sum_finish_axis1 (per facet row)"] = (
+            t3, 16.0 * (nsrc * m * m + m * xA), S * rows_local)
+        for r in range(1, nstrips):
+            core.sum_finish_axis(srcs, strips[r], axis=1, subgrid_off=sg.off1)
+        res = torch.empty((xA, xA), dtype=torch.complex128, device=dev)
+        row_offs = sorted({c.off0 for c in fcs})
+        srcs0 = [(strips[r], row_offs[r]) for r in range(nstrips)]
+        t4 = self._time(lambda: core.sum_finish_axis(srcs0, res, axis=0, subgrid_off=sg.off0))
+        out["sum_finish_axis0 (per subgrid)"] = (t4, 16.0 * (nstrips * m * xA + xA * xA), owned_sg)
+        kernels = []
+        total = sum(t * n for t, _, n in out.values())
+        for name, (t, by, n) in out.items():
+            ach = by / (t * 1e-3) / 1e9
+            kernels.append({
+                "kernel": name, "avg_ms": t, "launches_per_step": n,
+                "algorithmic_bytes_per_launch": by, "achieved": ach, "unit": "GB/s",
+                "frac": ach / hbm_gbs, "share_of_kernel_time": t * n / total,
+            })
+        dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
+        dominant = {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_gbs, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": None, "kernel": dom["kernel"],
+                    "avg_ms": dom["avg_ms"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
+        bmin = None
+        if step_ms:
+            by = 32.0 * MIB * self.contributions_per_step / self.world
+            ach = by / (step_ms * 1e-3) / 1e9
+            bmin = {"bytes_per_contribution": 32.0 * MIB, "achieved": ach, "unit": "GB/s",
+                    "frac": ach / hbm_gbs, "note": "end-to-end B_min of SURVEY.md section 8d per GPU"}
+        return {"kernels": kernels, "dominant": dominant, "bmin": bmin}
+
+    # ------------------------------------------------------------------ end to end (host buffers)
+    def e2e(self, steps=1, ring=4):
+        """Same transform through the public API with HOST buffers: facets start in pinned
+        host memory (H2D inside the timed region), every finished subgrid is copied to a
+        pinned host buffer (D2H inside the timed region)."""
+        yB, xA = self.yB, self.xA
+        host = {}
+        self.regenerate_facets()
+        for idx in self.local_idx:
+            h = torch.empty((yB, yB), dtype=torch.complex128, pin_memory=True)
+            h.copy_(self.facet_views[idx])
+            host[idx] = h
+        slots = [torch.empty((xA, xA), dtype=torch.complex128, pin_memory=True)
+                 for _ in range(ring)]
+        d2h = torch.cuda.Stream(self.device)
+        counter = {"n": 0, "bytes": 0}
+
+        def consumer(i, sg, tensor):
+            ev = torch.cuda.Event()
+            ev.record()
+            d2h.wait_event(ev)
+            with torch.cuda.stream(d2h):
+                slots[counter["n"] % ring].copy_(tensor, non_blocking=True)
+            tensor.record_stream(d2h)
+            counter["n"] += 1
+            counter["bytes"] += tensor.numel() * 16
+
+        times = []
+        for it in range(steps + 1):  # first pass is a warm-up
+            counter["n"] = counter["bytes"] = 0
+            self._barrier()
+            t0 = time.perf_counter()
+            self._run_forward(host, consumer=consumer)
+            self._barrier()
+            dt = time.perf_counter() - t0
+            if self.world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            if it > 0:
+                times.append(dt)
+        h2d = sum(h.numel() * 16 for h in host.values())
+        d2h_bytes = counter["bytes"]
+        if self.world > 1:
+            t = torch.tensor([h2d, d2h_bytes], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t)
+            h2d, d2h_bytes = float(t[0].item()), float(t[1].item())
+        sec = float(numpy.mean(times))
+        return {
+            "value": self.contributions_per_step / sec, "unit": "contributions/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_bytes),
+            "ms_per_step": sec * 1e3, "steps": steps,
+            "path": "SwiftlyForward(host pinned facets) -> get_subgrid_task -> pinned host "
+                    "subgrids; wall clock between device synchronisations, max over ranks",
+        }

@@ -22,31 +22,56 @@ int cuda_fail(cudaError_t e, const char* what) {
     return SWIFTLY_B200_ECUDA;
 }
 
-const cplx* twiddles(const swiftly_b200* h, int n) {
-    std::lock_guard<std::mutex> lock(h->mu);
-    auto it = h->tw.find(n);
-    if (it != h->tw.end()) return it->second;
-    std::vector<cplx> host((size_t)n);
-    const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int t = 0; t < n; ++t) {
-        long double a = two_pi * (long double)t / (long double)n;
-        host[t].x = (double)cosl(a);
-        host[t].y = (double)(-sinl(a));
-    }
+static const cplx* upload_table(const swiftly_b200* h, int key, const std::vector<cplx>& host) {
     cplx* dev = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dev, sizeof(cplx) * (size_t)n);
+    cudaError_t e = cudaMalloc((void**)&dev, sizeof(cplx) * host.size());
     if (e != cudaSuccess) {
         cuda_fail(e, "cudaMalloc(twiddles)");
         return nullptr;
     }
-    e = cudaMemcpy(dev, host.data(), sizeof(cplx) * (size_t)n, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(dev, host.data(), sizeof(cplx) * host.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaFree(dev);
         cuda_fail(e, "cudaMemcpy(twiddles)");
         return nullptr;
     }
-    h->tw[n] = dev;
+    h->tw[key] = dev;
     return dev;
+}
+
+static cplx unit_root(long double num, long double den) {  // exp(-2 pi i num / den)
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    long double a = two_pi * num / den;
+    cplx w;
+    w.x = (double)cosl(a);
+    w.y = (double)(-sinl(a));
+    return w;
+}
+
+// Compact per-pass table of the n-point Stockham plan (fft_engine.cuh): for every pass
+// after the first, with sub-transform size Ns (16, 256, 4096) and radix R, the Ns entries
+// exp(-2 pi i k / (Ns R)), k < Ns, stored pass after pass.
+const cplx* twiddles(const swiftly_b200* h, int n) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->tw.find(n);
+    if (it != h->tw.end()) return it->second;
+    std::vector<cplx> host;
+    for (int ns = 16; ns < n; ns *= 16) {
+        const int r = (n / ns >= 16) ? 16 : n / ns;
+        for (int k = 0; k < ns; ++k) host.push_back(unit_root(k, (long double)ns * r));
+    }
+    if (host.empty()) host.push_back(unit_root(0, 1));
+    return upload_table(h, n, host);
+}
+
+// Full table exp(-2 pi i t / n), t < n / 2 (split kernels: the radix-2 DIF pre-twiddle).
+const cplx* twiddles_full(const swiftly_b200* h, int n) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->tw.find(-n);
+    if (it != h->tw.end()) return it->second;
+    std::vector<cplx> host((size_t)(n / 2));
+    for (int t = 0; t < n / 2; ++t) host[t] = unit_root(t, n);
+    return upload_table(h, -n, host);
 }
 
 }  // namespace swiftly

@@ -37,7 +37,7 @@ int launch_lines(const swiftly_b200* h, const Op& op, bool line_fastest, cudaStr
 template <int H, int DIR, class Op>
 int launch_split(const swiftly_b200* h, const Op& op, cudaStream_t s) {
     const cplx* tw = twiddles(h, H);
-    const cplx* tw2 = twiddles(h, 2 * H);
+    const cplx* tw2 = twiddles_full(h, 2 * H);
     if (!tw || !tw2) return SWIFTLY_B200_ECUDA;
     SplitLineKernel<H, DIR, Op> k{op, tw, tw2};
     cudaError_t e = launch_body(k, grid_for(op.g.n_lines, 1), k.SMEM, s);

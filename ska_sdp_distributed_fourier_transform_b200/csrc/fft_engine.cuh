@@ -12,9 +12,15 @@
 // pass hands its output to a storer functor (scatter / accumulate / window
 // multiply), so a line makes exactly one trip HBM -> registers -> HBM.
 //
-// Twiddles come from a per-size table W_N^t = exp(-2 pi i t / N), t < N, in
-// global memory (L1/L2 resident, read through the read-only path); the
-// inverse direction conjugates on the fly.  The first pass needs none.
+// Twiddles: a pass with sub-transform size Ns and radix R multiplies input r of
+// butterfly j by w^r, w = exp(-2 pi i (j mod Ns) / (Ns R)).  Only w is loaded -- one
+// coalesced 16-byte load per butterfly from a compact per-pass table (Ns entries,
+// laid out pass after pass, < 4.4 K entries per FFT size) -- and the powers w^2..w^15
+// are formed in registers with 14 complex multiplies (product depth <= 3).  Loading
+// all 15 factors from a W_N^t table instead costs up to 16 L1 wavefronts per load
+// instruction and made the kernels LSU-bound (profiles/r01_*); the FP64 pipe has
+// the headroom.  The inverse direction conjugates on the fly; the first pass needs
+// no twiddles at all.
 //
 // Lines of 2N samples that do not fit shared memory (yN = 16384) are done as
 // two N-point transforms after one decimation-in-frequency radix-2 step that
@@ -129,6 +135,73 @@ struct FftCfg {
 
 SW_HD int sm_phys(int a) { return a + (a >> 4); }
 
+// offset of the pass with sub-transform size NS (16, 256 or 4096) in the compact table
+template <int NS>
+struct TwOffset {
+    static constexpr int V = TwOffset<NS / 16>::V + NS / 16;
+};
+template <>
+struct TwOffset<16> {
+    static constexpr int V = 0;
+};
+template <>
+struct TwOffset<1> {
+    static constexpr int V = 0;
+};
+
+SW_HD cplx csqr(cplx a) { return mk(a.x * a.x - a.y * a.y, (a.x + a.x) * a.y); }
+
+// v[r] *= w^r, r = 1..R-1
+template <int R>
+struct TwiddlePowers;
+template <>
+struct TwiddlePowers<2> {
+    static SW_HD void apply(cplx* v, cplx w1) { v[1] = cmul(v[1], w1); }
+};
+template <>
+struct TwiddlePowers<4> {
+    static SW_HD void apply(cplx* v, cplx w1) {
+        cplx w2 = csqr(w1);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], cmul(w2, w1));
+    }
+};
+template <>
+struct TwiddlePowers<8> {
+    static SW_HD void apply(cplx* v, cplx w1) {
+        cplx w2 = csqr(w1), w3 = cmul(w2, w1), w4 = csqr(w2);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1));
+        v[6] = cmul(v[6], cmul(w4, w2));
+        v[7] = cmul(v[7], cmul(w4, w3));
+    }
+};
+template <>
+struct TwiddlePowers<16> {
+    static SW_HD void apply(cplx* v, cplx w1) {
+        cplx w2 = csqr(w1), w3 = cmul(w2, w1), w4 = csqr(w2), w8 = csqr(w4), w12 = cmul(w8, w4);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1));
+        v[6] = cmul(v[6], cmul(w4, w2));
+        v[7] = cmul(v[7], cmul(w4, w3));
+        v[8] = cmul(v[8], w8);
+        v[9] = cmul(v[9], cmul(w8, w1));
+        v[10] = cmul(v[10], cmul(w8, w2));
+        v[11] = cmul(v[11], cmul(w8, w3));
+        v[12] = cmul(v[12], w12);
+        v[13] = cmul(v[13], cmul(w12, w1));
+        v[14] = cmul(v[14], cmul(w12, w2));
+        v[15] = cmul(v[15], cmul(w12, w3));
+    }
+};
+
 template <int N, int NS>
 struct PassRadix {
     static constexpr int R = (N / NS >= 16) ? 16 : (N / NS);
@@ -137,7 +210,7 @@ struct PassRadix {
 // Stockham passes from sub-transform size NS up to N (recursive over passes).
 //   lt  : thread index within the line group, 0 <= lt < T
 //   sm  : this line's shared memory buffer (FftCfg<N>::PADDED slots)
-//   tw  : table exp(-2 pi i t / N), t < N
+//   tw  : compact per-pass twiddle table of size N (see twiddles() in capi.cu)
 //   ld(q)    -> cplx   natural-order input sample q   (FIRST pass only)
 //   st(p, v)          natural-order output sample p  (LAST pass only)
 //   sync()            CTA barrier
@@ -167,13 +240,9 @@ SW_HD void stockham_passes(int lt, cplx* sm, const cplx* tw, Ld& ld, St& st, Syn
         const int j = lt + it * T;
         if (!FIRST) {
             const int k = j & (NS - 1);
-            constexpr int TSTRIDE = N / (NS * R);
-#pragma unroll
-            for (int r = 1; r < R; ++r) {
-                cplx w = ldg_c(tw + r * k * TSTRIDE);
-                if (DIR > 0) w.y = -w.y;
-                v[it][r] = cmul(v[it][r], w);
-            }
+            cplx w1 = ldg_c(tw + TwOffset<NS>::V + k);
+            if (DIR > 0) w1.y = -w1.y;
+            TwiddlePowers<R>::apply(v[it], w1);
         }
         Radix<R, DIR>::run(v[it]);
         const int base = (j / NS) * (NS * R) + (j & (NS - 1));

@@ -15,7 +15,7 @@ struct swiftly_b200 {
     int device;
     double* d_Fb;  // yN - 1
     double* d_Fn;  // m
-    // twiddle tables exp(-2 pi i t / n), t < n, keyed by n
+    // twiddle tables keyed by n (compact per-pass table) or -n (full table, t < n/2)
     mutable std::mutex mu;
     mutable std::map<int, swiftly::cplx*> tw;
     int force_split;  // debug / test: transform yN lines with the 2 x yN/2 split path
@@ -28,6 +28,8 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // returns the table for size n (creating it on first use), nullptr on failure
 const cplx* twiddles(const swiftly_b200* h, int n);
+// full table exp(-2 pi i t / n), t < n / 2
+const cplx* twiddles_full(const swiftly_b200* h, int n);
 
 // largest directly supported power-of-two line length (fits shared memory)
 static const int MAX_DIRECT_FFT = 8192;

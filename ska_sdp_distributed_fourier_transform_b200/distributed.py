@@ -1,0 +1,200 @@
+"""
+Multi-GPU facet -> subgrid transform: one process per GPU, facets sharded.
+
+The reference distributes one task per facet over Dask workers and ships every
+``(m, m)`` contribution over TCP to the worker that sums a subgrid
+(``api.py:263-277``).  Here the facets are partitioned over the ranks
+of a ``torch.distributed`` process group (NCCL over NVLink on the B200 box); each
+rank keeps its facets' ``BF_F`` / ``NMBF_BF`` resident and, per subgrid, reduces
+its facets along axis 1 *locally* into compact strips (``(m, xA)`` per distinct
+facet ``off0`` on the rank -- the fused ``sum_finish_axis`` kernel).  The only data
+exchange is those strips: subgrids are processed in batches of ``world_size``,
+subgrid ``b`` of a batch is owned by rank ``b``, one ``all_to_all`` per batch moves
+every rank's strips to the owners, and each owner runs the axis-0 kernel over the
+strips of all ranks.  Per subgrid a rank sends ``n_local_rows * m * xA * 16`` bytes
+(32 MiB at cfg4 on 8 GPUs) -- half of what reducing finished partial subgrids would
+move and without replicating the axis-0 work.  The exchange of batch ``k`` runs on
+the communication stream while the compute stream produces the strips of batch
+``k + 1`` and finishes the subgrids of batch ``k - 1``.
+
+Calls are collective (SPMD): every rank must call ``get_subgrid_tasks`` with the same
+subgrid list.
+"""
+
+import collections
+
+import torch
+import torch.distributed as dist
+
+from .api import DeviceTask, _device_mask, _device_of, _LRU, _upload_iter
+
+
+def partition_facets(facet_configs, world_size):
+    """Owner rank of every facet: facets sorted by (off0, off1), split contiguously.
+
+    For a full cover with ``rows % world_size == 0`` a rank owns whole facet rows; for a
+    sparse cover rows are split so that no rank idles (only the sum over facets matters).
+    """
+    order = sorted(range(len(facet_configs)),
+                   key=lambda i: (facet_configs[i].off0, facet_configs[i].off1))
+    owner = [0] * len(facet_configs)
+    n = len(order)
+    for pos, idx in enumerate(order):
+        owner[idx] = min(world_size - 1, pos * world_size // max(n, 1))
+    return owner
+
+
+class SwiftlyForwardSharded:
+    """Facet -> subgrid transform with facets sharded over a process group.
+
+    :param swiftly_config: ``SwiftlyConfig`` (its core lives on this rank's GPU)
+    :param facet_configs: ALL facet configs (identical on every rank)
+    :param local_facets: ``{facet index: data}`` for the facets this rank owns
+        (see :func:`partition_facets`)
+    :param lru_forward: resident subgrid columns
+    :param group: process group (default: world)
+    :param bf_f_buffers: optional ``{facet index: (yN, size) tensor}`` outputs of stage 1
+    """
+
+    # pylint: disable=too-many-instance-attributes,too-many-arguments
+    def __init__(self, swiftly_config, facet_configs, local_facets, lru_forward=1, group=None,
+                 bf_f_buffers=None):
+        self.config = swiftly_config
+        self.core = swiftly_config.core
+        self.device = _device_of(self.core)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.facet_configs = list(facet_configs)
+        self.owner = partition_facets(self.facet_configs, self.world)
+        self.local_idx = [i for i, o in enumerate(self.owner) if o == self.rank]
+        missing = [i for i in self.local_idx if i not in local_facets]
+        if missing:
+            raise ValueError(f"rank {self.rank} owns facets {missing} but got no data for them")
+        self._local_facets = dict(local_facets)
+        self._bf_f_buffers = bf_f_buffers or {}
+        self.lru = _LRU(lru_forward)
+        self.BF_Fs = None
+        # strip layout: for every rank the sorted distinct off0 of its facets
+        self.rank_rows = []
+        for r in range(self.world):
+            offs = sorted({self.facet_configs[i].off0
+                           for i, o in enumerate(self.owner) if o == r})
+            self.rank_rows.append(offs)
+        self.rows_max = max(1, max(len(r) for r in self.rank_rows))
+        self.my_rows = self.rank_rows[self.rank]
+        self._bufs = {}
+        self.launches = 0
+
+    # ------------------------------------------------------------------ local stages
+    def _prepare(self):
+        if self.BF_Fs is None:
+            self.BF_Fs = {}
+            uploads = _upload_iter([self._local_facets[i] for i in self.local_idx], self.device)
+            for i, facet in zip(self.local_idx, uploads):
+                cfg = self.facet_configs[i]
+                self.BF_Fs[i] = self.core.prepare_facet(
+                    facet, cfg.off0, axis=0, out=self._bf_f_buffers.get(i))
+                self.launches += 1
+                del facet
+            self._local_facets = {}
+        return self.BF_Fs
+
+    def _column(self, off0):
+        cached = self.lru.get(off0)
+        if cached is None:
+            reuse = None
+            if len(self.lru.data) >= self.lru.size:
+                _, reuse = self.lru.data.popitem(last=False)
+            cached = {}
+            for i in self.local_idx:
+                buf = None if reuse is None else reuse[i]
+                cached[i] = self.core.extract_column(
+                    self.BF_Fs[i], off0, self.facet_configs[i].off1, out=buf)
+                self.launches += 1
+            self.lru.set(off0, cached)
+        return cached
+
+    def _buffers(self, slot, xA):
+        key = (slot, xA)
+        if key not in self._bufs:
+            m = self.core.xM_yN_size
+            shape = (self.world, self.rows_max, m, xA)
+            send = torch.zeros(shape, dtype=torch.complex128, device=self.device)
+            recv = torch.zeros(shape, dtype=torch.complex128, device=self.device)
+            self._bufs[key] = (send, recv)
+        return self._bufs[key]
+
+    def _local_strips(self, sg, out):
+        """Axis-1 reduction of this rank's facets for subgrid ``sg`` into ``out[row]``."""
+        column = self._column(sg.off0)
+        mask1 = _device_mask(sg.mask1, self.device)
+        for r, off0 in enumerate(self.my_rows):
+            members = [i for i in self.local_idx if self.facet_configs[i].off0 == off0]
+            self.core.sum_finish_axis(
+                [(column[i], self.facet_configs[i].off1) for i in members],
+                out[r], axis=1, subgrid_off=sg.off1, mask=mask1)
+            self.launches += 1
+
+    def _finish(self, sg, recv):
+        """Axis-0 reduction over the strips of all ranks (owner only)."""
+        sources = []
+        for r in range(self.world):
+            for k, off0 in enumerate(self.rank_rows[r]):
+                sources.append((recv[r, k], off0))
+        out = torch.empty((sg.size, sg.size), dtype=torch.complex128, device=self.device)
+        self.core.sum_finish_axis(sources, out, axis=0, subgrid_off=sg.off0,
+                                  mask=_device_mask(sg.mask0, self.device))
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ collective driver
+    def get_subgrid_tasks(self, subgrid_configs, consumer=None):
+        """Transform all ``subgrid_configs`` (collective call).
+
+        Returns ``{index in subgrid_configs: DeviceTask}`` for the subgrids this rank owns
+        (subgrid ``i`` is owned by rank ``i % world_size``).  ``consumer(index, config,
+        tensor)``, if given, is called for every owned subgrid instead of keeping it.
+        """
+        subgrid_configs = list(subgrid_configs)
+        self._prepare()
+        results = {}
+        if not subgrid_configs:
+            return results
+        sizes = {sg.size for sg in subgrid_configs}
+        if len(sizes) != 1:
+            raise ValueError("all subgrids of one call must have the same size")
+        xA = sizes.pop()
+        batches = [subgrid_configs[i:i + self.world]
+                   for i in range(0, len(subgrid_configs), self.world)]
+        pending = None  # (batch index, work, recv buffer)
+
+        def finish(bi, work, recv):
+            if work is not None:
+                work.wait()
+            batch = batches[bi]
+            if self.rank < len(batch):
+                idx = bi * self.world + self.rank
+                out = self._finish(batch[self.rank], recv)
+                if consumer is not None:
+                    consumer(idx, batch[self.rank], out)
+                else:
+                    results[idx] = DeviceTask(out)
+
+        for bi, batch in enumerate(batches):
+            send, recv = self._buffers(bi % 2, xA)
+            for b, sg in enumerate(batch):
+                self._local_strips(sg, send[b])
+            work = None
+            if self.world > 1:
+                work = dist.all_to_all_single(
+                    torch.view_as_real(recv).reshape(self.world, -1),
+                    torch.view_as_real(send).reshape(self.world, -1),
+                    group=self.group, async_op=True)
+            else:
+                recv = send
+            if pending is not None:
+                finish(*pending)
+            pending = (bi, work, recv)
+        finish(*pending)
+        return results

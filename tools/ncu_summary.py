@@ -1,0 +1,43 @@
+"""Print the key metrics of an .ncu-rep (raw page) -- dev tool."""
+import csv
+import subprocess
+import sys
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread',
+        'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor',
+        'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'sm__inst_executed_pipe_fp64.sum',
+        'sm__inst_executed_pipe_lsu.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+        'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'smsp__warps_eligible.avg.per_cycle_active',
+        'sm__cycles_elapsed.max', 'smsp__cycles_active.avg',
+        'local_load', 'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum']
+STALL = 'smsp__average_warp'
+
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr = rows[0]
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    print(d.get('Kernel Name', '')[:150])
+    for k in KEYS:
+        if k in d:
+            print(f"   {k} = {d[k]}")
+    st = sorted(((float(v.replace(',', '')), k) for k, v in d.items()
+                 if k.startswith('smsp__average_warps_issue_stalled') and v not in ('', 'n/a')), reverse=True)
+    for v, k in st[:7]:
+        print(f"   STALL(warps per issue) {k.replace('smsp__average_warps_issue_stalled_','').replace('_per_issue_active.ratio','')} = {v:.2f}")
