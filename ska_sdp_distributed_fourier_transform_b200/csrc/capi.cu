@@ -74,6 +74,27 @@ const cplx* twiddles_full(const swiftly_b200* h, int n) {
     return upload_table(h, -n, host);
 }
 
+cplx* split_scratch(const swiftly_b200* h, cudaStream_t s, size_t samples) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto& slot = h->scratch[s];
+    if (slot.first && slot.second >= samples) return slot.first;
+    if (slot.first) {
+        cudaStreamSynchronize(s);  // kernels on this stream may still use the old buffer
+        cudaFree(slot.first);
+        slot.first = nullptr;
+        slot.second = 0;
+    }
+    cplx* dev = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dev, sizeof(cplx) * samples);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaMalloc(split scratch)");
+        return nullptr;
+    }
+    slot.first = dev;
+    slot.second = samples;
+    return dev;
+}
+
 }  // namespace swiftly
 
 // ------------------------------------------------------------------ plan
@@ -135,6 +156,8 @@ extern "C" void swiftly_b200_destroy(swiftly_b200* h) {
     if (h->d_Fb) cudaFree(h->d_Fb);
     if (h->d_Fn) cudaFree(h->d_Fn);
     for (auto& kv : h->tw) cudaFree(kv.second);
+    for (auto& kv : h->scratch)
+        if (kv.second.first) cudaFree(kv.second.first);
     delete h;
 }
 

@@ -63,6 +63,24 @@ SW_HD double ldg_d(const double* p) {
 #endif
 }
 
+// streaming global accesses: data that is touched once per kernel (inputs and outputs are
+// far larger than the 126 MB L2) should not push the few reused lines (twiddle / window
+// tables, split-kernel scratch) out of L2
+SW_HD cplx ld_stream(const cplx* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+SW_HD void st_stream(cplx* p, cplx v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // non-negative modulo for possibly negative a, n > 0
 SW_HD int64_t pmod(int64_t a, int64_t n) {
     int64_t r = a % n;

@@ -39,8 +39,12 @@ int launch_split(const swiftly_b200* h, const Op& op, cudaStream_t s) {
     const cplx* tw = twiddles(h, H);
     const cplx* tw2 = twiddles_full(h, 2 * H);
     if (!tw || !tw2) return SWIFTLY_B200_ECUDA;
-    SplitLineKernel<H, DIR, Op> k{op, tw, tw2};
-    cudaError_t e = launch_body(k, grid_for(op.g.n_lines, 1), k.SMEM, s);
+    // persistent CTAs: two per SM's worth of lines in flight keeps the scratch L2 resident
+    int64_t blocks = op.g.n_lines < 296 ? op.g.n_lines : 296;
+    cplx* scratch = split_scratch(h, s, (size_t)blocks * H);
+    if (!scratch) return SWIFTLY_B200_ECUDA;
+    SplitLineKernel<H, DIR, Op> k{op, tw, tw2, scratch};
+    cudaError_t e = launch_body(k, (int)blocks, k.SMEM, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "split line FFT kernel launch");
 }
 

@@ -3,14 +3,14 @@
 // One "line" (a 1-D transform of N complex128 samples, N a power of two,
 // 16 <= N <= 8192) is transformed by T = N/16 threads with the Stockham
 // autosort algorithm: radix-16 passes (and one final radix-2/4/8 pass when
-// log2 N is not a multiple of 4).  Each pass holds its 16 samples in
-// registers, the exchange between passes goes through shared memory
-// (padded by one 16-byte slot per 16 to make the stride-16 scatter of the
-// first pass conflict free).  The FIRST pass reads its input through a
-// caller-supplied loader functor (global memory gather: window multiply,
-// zero padding and cyclic shifts are index arithmetic there) and the LAST
-// pass hands its output to a storer functor (scatter / accumulate / window
-// multiply), so a line makes exactly one trip HBM -> registers -> HBM.
+// log2 N is not a multiple of 4).  Every thread keeps its 16 samples in registers
+// for the whole transform; between passes the samples change owner through a
+// shared-memory exchange buffer of N (+1/16 padding) DOUBLES: real parts first,
+// then imaginary parts through the same buffer.  The FIRST pass reads its input
+// through a caller-supplied loader functor (global memory gather: window multiply,
+// zero padding and cyclic shifts are index arithmetic there) and the LAST pass
+// hands its output to a storer functor (scatter / accumulate / window multiply),
+// so a line makes exactly one trip HBM -> registers -> HBM.
 //
 // Twiddles: a pass with sub-transform size Ns and radix R multiplies input r of
 // butterfly j by w^r, w = exp(-2 pi i (j mod Ns) / (Ns R)).  Only w is loaded -- one
@@ -130,10 +130,17 @@ template <int N>
 struct FftCfg {
     static_assert(N >= 16 && (N & (N - 1)) == 0, "FFT size must be a power of two >= 16");
     static constexpr int T = N / 16;           // threads per line
-    static constexpr int PADDED = N + N / 16;  // smem slots (16 B each) per line
+    static constexpr int PADDED = N + N / 16;  // shared memory DOUBLES per line
 };
 
+// exchange buffer index: one pad slot per 16 keeps the stride-16 scatter of the first
+// pass conflict free (17 j + r hits 16 distinct 8-byte bank pairs per half warp)
 SW_HD int sm_phys(int a) { return a + (a >> 4); }
+
+template <int N, int NS>
+struct PassRadix {
+    static constexpr int R = (N / NS >= 16) ? 16 : (N / NS);
+};
 
 // offset of the pass with sub-transform size NS (16, 256 or 4096) in the compact table
 template <int NS>
@@ -202,69 +209,101 @@ struct TwiddlePowers<16> {
     }
 };
 
-template <int N, int NS>
-struct PassRadix {
-    static constexpr int R = (N / NS >= 16) ? 16 : (N / NS);
-};
-
-// Stockham passes from sub-transform size NS up to N (recursive over passes).
-//   lt  : thread index within the line group, 0 <= lt < T
-//   sm  : this line's shared memory buffer (FftCfg<N>::PADDED slots)
-//   tw  : compact per-pass twiddle table of size N (see twiddles() in capi.cu)
-//   ld(q)    -> cplx   natural-order input sample q   (FIRST pass only)
-//   st(p, v)          natural-order output sample p  (LAST pass only)
-//   sync()            CTA barrier
-template <int N, int NS, int DIR, class Ld, class St, class Sync>
-SW_HD void stockham_passes(int lt, cplx* sm, const cplx* tw, Ld& ld, St& st, Sync& sync) {
+// Passes from sub-transform size NS (> 1) to N.  On entry v[it * RP + r] holds the OUTPUT
+// of the previous pass (radix RP, sub-transform size NS / RP) in registers: output r of
+// butterfly j = lt + it * T, which belongs at exchange index (j / NSP) * NS + j % NSP + r * NSP.
+// The exchange through shared memory moves real parts, then imaginary parts, through ONE
+// buffer of N (+ padding) doubles -- half the footprint of a complex exchange, which is what
+// lets two CTAs of the big kernels share an SM; every thread keeps its 16 samples in
+// registers throughout.
+template <int N, int NS, int RP, int DIR, class St, class Sync>
+SW_HD void stockham_tail(int lt, double* sm, const cplx* tw, cplx* v, St& st, Sync& sync) {
     constexpr int T = FftCfg<N>::T;
+    constexpr int NSP = NS / RP;
+    constexpr int ITP = 16 / RP;
     constexpr int R = PassRadix<N, NS>::R;
-    constexpr int NB = N / R;  // butterflies in this pass
-    constexpr bool FIRST = (NS == 1);
+    constexpr int NB = N / R;
+    constexpr int ITERS = 16 / R;
     constexpr bool LAST = (NS * R == N);
-    constexpr int ITERS = NB / T;  // NB = N/R >= N/16 = T, both powers of two
-    cplx v[ITERS][R];
+    double nx[16];
+#pragma unroll
+    for (int it = 0; it < ITP; ++it) {
+        const int j = lt + it * T;
+        const int base = (j / NSP) * NS + (j & (NSP - 1));
+#pragma unroll
+        for (int r = 0; r < RP; ++r) sm[sm_phys(base + r * NSP)] = v[it * RP + r].x;
+    }
+    sync();
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
         const int j = lt + it * T;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (FIRST)
-                v[it][r] = ld(j + r * NB);
-            else
-                v[it][r] = sm[sm_phys(j + r * NB)];
-        }
+        for (int r = 0; r < R; ++r) nx[it * R + r] = sm[sm_phys(j + r * NB)];
     }
-    if (!FIRST && !LAST) sync();  // everybody has read before anybody overwrites
+    sync();
+#pragma unroll
+    for (int it = 0; it < ITP; ++it) {
+        const int j = lt + it * T;
+        const int base = (j / NSP) * NS + (j & (NSP - 1));
+#pragma unroll
+        for (int r = 0; r < RP; ++r) sm[sm_phys(base + r * NSP)] = v[it * RP + r].y;
+    }
+    sync();
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
         const int j = lt + it * T;
-        if (!FIRST) {
-            const int k = j & (NS - 1);
-            cplx w1 = ldg_c(tw + TwOffset<NS>::V + k);
-            if (DIR > 0) w1.y = -w1.y;
-            TwiddlePowers<R>::apply(v[it], w1);
-        }
-        Radix<R, DIR>::run(v[it]);
-        const int base = (j / NS) * (NS * R) + (j & (NS - 1));
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (LAST)
-                st(base + r * NS, v[it][r]);
-            else
-                sm[sm_phys(base + r * NS)] = v[it][r];
-        }
+        for (int r = 0; r < R; ++r) v[it * R + r] = mk(nx[it * R + r], sm[sm_phys(j + r * NB)]);
     }
-    if constexpr (!LAST) {
-        sync();
-        stockham_passes<N, NS * R, DIR>(lt, sm, tw, ld, st, sync);
+    // twiddle + butterflies of this pass
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = lt + it * T;
+        const int k = j & (NS - 1);
+        cplx w1 = ldg_c(tw + TwOffset<NS>::V + k);
+        if (DIR > 0) w1.y = -w1.y;
+        TwiddlePowers<R>::apply(v + it * R, w1);
+        Radix<R, DIR>::run(v + it * R);
+    }
+    if constexpr (LAST) {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int j = lt + it * T;
+            const int base = (j / NS) * (NS * R) + (j & (NS - 1));
+#pragma unroll
+            for (int r = 0; r < R; ++r) st(base + r * NS, v[it * R + r]);
+        }
+    } else {
+        sync();  // everybody has read the imaginary parts before the buffer is rewritten
+        stockham_tail<N, NS * R, R, DIR>(lt, sm, tw, v, st, sync);
     }
 }
 
-// Full N-point transform of one line.  The caller guarantees that nobody is
-// still reading `sm` from a previous line (sync before re-use).
+// Full N-point transform of one line.
+//   lt  : thread index within the line group, 0 <= lt < T = N/16
+//   sm  : this line's exchange buffer, FftCfg<N>::PADDED doubles
+//   tw  : compact per-pass twiddle table of size N (see twiddles() in capi.cu)
+//   ld(q)    -> cplx   natural-order input sample q
+//   st(p, v)          natural-order output sample p
+//   sync()            CTA barrier
+// The caller guarantees that nobody is still reading `sm` from a previous line (barrier
+// before re-use).
 template <int N, int DIR, class Ld, class St, class Sync>
-SW_HD void line_fft(int lt, cplx* sm, const cplx* tw, Ld& ld, St& st, Sync& sync) {
-    stockham_passes<N, 1, DIR>(lt, sm, tw, ld, st, sync);
+SW_HD void line_fft(int lt, double* sm, const cplx* tw, Ld& ld, St& st, Sync& sync) {
+    constexpr int T = FftCfg<N>::T;
+    constexpr int R = PassRadix<N, 1>::R;  // 16
+    constexpr int NB = N / R;
+    cplx v[16];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = ld(lt + r * NB);
+    Radix<R, DIR>::run(v);
+    if constexpr (R == N) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) st(lt * R + r, v[r]);  // N == 16: lt == 0
+    } else {
+        stockham_tail<N, R, R, DIR>(lt, sm, tw, v, st, sync);
+    }
+    (void)T;
 }
 
 }  // namespace swiftly

@@ -52,11 +52,11 @@ struct PrepareFacetOp {
         if (k >= fs) return mk(0.0, 0.0);
         int64_t row = rm_m ? (int64_t)wrap_add(rm_base, wrap_sub((int)line, rm_s_m, rm_m), rm_mod)
                            : line;
-        return cscale(ldg_c(g.in + row * g.in_ls + (int64_t)k * g.in_es), ldg_d(fb + k));
+        return cscale(ld_stream(g.in + row * g.in_ls + (int64_t)k * g.in_es), ldg_d(fb + k));
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, n / 2, n);
-        g.out[line * g.out_ls + (int64_t)pc * g.out_es] = cscale(v, scale);
+        st_stream(g.out + line * g.out_ls + (int64_t)pc * g.out_es, cscale(v, scale));
     }
 };
 
@@ -69,14 +69,14 @@ struct FinishFacetOp {
     const double* mask;  // optional 0/1 facet mask along the axis (api_helper.py:175-176,195-196)
     SW_HD cplx load(int64_t line, int q) const {
         int qc = wrap_add(q, n / 2, n);
-        return ldg_c(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
+        return ld_stream(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, n / 2, n);
         int k = wrap_sub(pc, start, n);
         if (k < fs) {
             double s = mask ? ldg_d(fb + k) * ldg_d(mask + k) : ldg_d(fb + k);
-            g.out[line * g.out_ls + (int64_t)k * g.out_es] = cscale(v, s);
+            st_stream(g.out + line * g.out_ls + (int64_t)k * g.out_es, cscale(v, s));
         }
     }
 };
@@ -91,7 +91,7 @@ struct AddToSubgridOp {
     int base;  // (xM/2 - m/2 + sf) mod xM
     SW_HD cplx load(int64_t line, int t) const {
         int tc = wrap_add(t, m / 2, m);
-        return ldg_c(g.in + line * g.in_ls + (int64_t)tc * g.in_es);
+        return ld_stream(g.in + line * g.in_ls + (int64_t)tc * g.in_es);
     }
     SW_HD void store(int64_t line, int w, cplx v) const {
         int wc = wrap_add(w, m / 2, m);
@@ -116,11 +116,11 @@ struct ExtractFromSubgridOp {
         int tc = wrap_add(t, m / 2, m);
         int u = wrap_sub(tc, sf_m, m);
         int pos = wrap_add(base, u, xM);
-        return cscale(ldg_c(g.in + line * g.in_ls + (int64_t)pos * g.in_es), ldg_d(fn + u));
+        return cscale(ld_stream(g.in + line * g.in_ls + (int64_t)pos * g.in_es), ldg_d(fn + u));
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, m / 2, m);
-        g.out[line * g.out_ls + (int64_t)pc * g.out_es] = cscale(v, scale);
+        st_stream(g.out + line * g.out_ls + (int64_t)pc * g.out_es, cscale(v, scale));
     }
 };
 
@@ -134,14 +134,14 @@ struct FinishSubgridOp {
     const double* mask;  // optional 0/1 mask along the axis (api_helper.py:107-111) or null
     SW_HD cplx load(int64_t line, int q) const {
         int qc = wrap_add(q, xM / 2, xM);
-        return ldg_c(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
+        return ld_stream(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, xM / 2, xM);
         int r = wrap_sub(pc, start, xM);
         if (r < sz) {
             double s = mask ? scale * ldg_d(mask + r) : scale;
-            g.out[line * g.out_ls + (int64_t)r * g.out_es] = cscale(v, s);
+            st_stream(g.out + line * g.out_ls + (int64_t)r * g.out_es, cscale(v, s));
         }
     }
 };
@@ -156,11 +156,11 @@ struct PrepareSubgridOp {
         int qc = wrap_add(q, xM / 2, xM);
         int r = wrap_sub(qc, start, xM);
         if (r >= sz) return mk(0.0, 0.0);
-        return ldg_c(g.in + line * g.in_ls + (int64_t)r * g.in_es);
+        return ld_stream(g.in + line * g.in_ls + (int64_t)r * g.in_es);
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, xM / 2, xM);
-        g.out[line * g.out_ls + (int64_t)pc * g.out_es] = v;
+        st_stream(g.out + line * g.out_ls + (int64_t)pc * g.out_es, v);
     }
 };
 
@@ -176,16 +176,16 @@ struct LineKernel {
     static constexpr int THREADS = T * LPC;
     // odd slot stride between line buffers => lines land in different banks
     static constexpr int LSTRIDE = FftCfg<NFFT>::PADDED | 1;
-    static constexpr size_t SMEM = (size_t)LSTRIDE * LPC * sizeof(cplx);
+    static constexpr size_t SMEM = (size_t)LSTRIDE * LPC * sizeof(double);
     Op op;
     const cplx* tw;
 
     template <class Ctx>
     SW_HD void operator()(Ctx& ctx) const {
-        cplx* smem = (cplx*)ctx.smem;
+        double* smem = (double*)ctx.smem;
         const int l = LINE_FASTEST ? (ctx.tid % LPC) : (ctx.tid / T);
         const int lt = LINE_FASTEST ? (ctx.tid / LPC) : (ctx.tid % T);
-        cplx* sm = smem + (size_t)l * LSTRIDE;
+        double* sm = smem + (size_t)l * LSTRIDE;
         auto sync = [&]() { ctx.sync(); };
         for (int64_t line0 = (int64_t)ctx.bid * LPC; line0 < op.g.n_lines;
              line0 += (int64_t)ctx.nblocks * LPC) {
@@ -201,39 +201,49 @@ struct LineKernel {
     }
 };
 
-// 2*H-point transform as two H-point transforms after one radix-2
-// decimation-in-frequency step folded into the loader:
-//   X[2k]   = FFT_H( z[j] + z[j+H] )[k]
-//   X[2k+1] = FFT_H( (z[j] - z[j+H]) * W_2H^(DIR j) )[k]
-// tw2 is the 2H-point table, tw the H-point table.  One line per CTA.
+// 2*H-point transform as two H-point transforms (lines that do not fit shared memory,
+// yN = 16384), decimation in time:
+//   E = FFT_H(z[2j]),  O = FFT_H(z[2j+1]),  w = exp(DIR 2 pi i k / 2H)
+//   X[k] = E[k] + w O[k],   X[k+H] = E[k] - w O[k]
+// E is parked in a per-CTA global scratch line (H samples, L2 resident; every thread reads
+// back exactly the samples it wrote, so no synchronisation is involved) while O is
+// computed; both halves of the output are then written with unit stride.  (A
+// decimation-in-frequency split needs no scratch but writes X[2k] and X[2k+1] in
+// separate passes: 16-byte stores at 32-byte stride cost 3x the DRAM write traffic,
+// profiles/r01_f2_split_dif.txt.)  tw2 is the table exp(-2 pi i t / 2H), t < H.
 template <int H, int DIR, class Op>
 struct SplitLineKernel {
     static constexpr int T = FftCfg<H>::T;
     static constexpr int THREADS = T;
-    static constexpr size_t SMEM = (size_t)FftCfg<H>::PADDED * sizeof(cplx);
+    static constexpr size_t SMEM = (size_t)FftCfg<H>::PADDED * sizeof(double);
     Op op;
-    const cplx* tw;   // size H
-    const cplx* tw2;  // size 2H
+    const cplx* tw;   // compact table of the H-point plan
+    const cplx* tw2;  // exp(-2 pi i t / 2H), t < H
+    cplx* scratch;    // gridDim.x * H samples
 
     template <class Ctx>
     SW_HD void operator()(Ctx& ctx) const {
-        cplx* sm = (cplx*)ctx.smem;
+        double* sm = (double*)ctx.smem;
+        cplx* stash = scratch + (size_t)ctx.bid * H;
         const int lt = ctx.tid;
         auto sync = [&]() { ctx.sync(); };
         for (int64_t line = ctx.bid; line < op.g.n_lines; line += ctx.nblocks) {
             {
-                auto ld = [&](int q) { return cadd(op.load(line, q), op.load(line, q + H)); };
-                auto st = [&](int p, cplx v) { op.store(line, 2 * p, v); };
+                auto ld = [&](int q) { return op.load(line, 2 * q); };
+                auto st = [&](int k, cplx v) { stash[k] = v; };
                 line_fft<H, DIR>(lt, sm, tw, ld, st, sync);
             }
             ctx.sync();
             {
-                auto ld = [&](int q) {
-                    cplx w = ldg_c(tw2 + q);
+                auto ld = [&](int q) { return op.load(line, 2 * q + 1); };
+                auto st = [&](int k, cplx o) {
+                    cplx w = ldg_c(tw2 + k);
                     if (DIR > 0) w.y = -w.y;
-                    return cmul(csub(op.load(line, q), op.load(line, q + H)), w);
+                    cplx e = stash[k];
+                    cplx wo = cmul(o, w);
+                    op.store(line, k, cadd(e, wo));
+                    op.store(line, k + H, csub(e, wo));
                 };
-                auto st = [&](int p, cplx v) { op.store(line, 2 * p + 1, v); };
                 line_fft<H, DIR>(lt, sm, tw, ld, st, sync);
             }
             ctx.sync();
@@ -268,13 +278,13 @@ struct WindowCopyKernel {
             }
             int w = wrap_add(base, wrap_sub(t, s_m, m), yN);
             if (SCATTER_ADD) {
-                cplx v = ldg_c(g.in + line * g.in_ls + (int64_t)t * g.in_es);
+                cplx v = ld_stream(g.in + line * g.in_ls + (int64_t)t * g.in_es);
                 cplx* o = g.out + line * g.out_ls + (int64_t)w * g.out_es;
                 cplx a = *o;
                 *o = cadd(a, v);
             } else {
                 g.out[line * g.out_ls + (int64_t)t * g.out_es] =
-                    ldg_c(g.in + line * g.in_ls + (int64_t)w * g.in_es);
+                    ld_stream(g.in + line * g.in_ls + (int64_t)w * g.in_es);
             }
         }
     }
@@ -311,9 +321,9 @@ struct SubgridAxisKernel {
     static constexpr int THREADS = FftCfg<XM>::T;
     static constexpr int CONC = THREADS / T_M;  // = XM / M concurrent m-point transforms
     static constexpr int WSTRIDE = FftCfg<M>::PADDED | 1;
-    static constexpr int WORK = CONC * WSTRIDE;  // >= FftCfg<XM>::PADDED
+    static constexpr int WORK = CONC * WSTRIDE;  // doubles, >= FftCfg<XM>::PADDED
     static_assert(WORK >= FftCfg<XM>::PADDED, "work area must hold the xM exchange buffer");
-    static constexpr size_t SMEM = (size_t)(XM + WORK) * sizeof(cplx);
+    static constexpr size_t SMEM = (size_t)XM * sizeof(cplx) + (size_t)WORK * sizeof(double);
 
     SgSource src[SW_MAX_SOURCES];
     int n_slots;
@@ -330,7 +340,7 @@ struct SubgridAxisKernel {
     template <class Ctx>
     SW_HD void operator()(Ctx& ctx) const {
         cplx* acc = (cplx*)ctx.smem;
-        cplx* work = acc + XM;
+        double* work = (double*)(acc + XM);
         const int c = ctx.tid / T_M;
         const int lt = ctx.tid % T_M;
         auto sync = [&]() { ctx.sync(); };
@@ -352,7 +362,7 @@ struct SubgridAxisKernel {
                     if (!active) return mk(0.0, 0.0);
                     int tc = wrap_add(t, M / 2, M);
                     int idx = wrap_add(wbase, wrap_sub(tc, s_m, M), wmod);
-                    return ldg_c(base + (int64_t)idx * es);
+                    return ld_stream(base + (int64_t)idx * es);
                 };
                 auto st = [&](int w, cplx v) {
                     if (!active) return;
@@ -374,7 +384,7 @@ struct SubgridAxisKernel {
                     int r = wrap_sub(pc, start, XM);
                     if (r < sz) {
                         double f = mask ? scale * ldg_d(mask + r) : scale;
-                        o[(int64_t)r * out_es] = cscale(v, f);
+                        st_stream(o + (int64_t)r * out_es, cscale(v, f));
                     }
                 };
                 line_fft<XM, +1>(ctx.tid, work, tw_x, ld, st, sync);

@@ -18,6 +18,8 @@ struct swiftly_b200 {
     // twiddle tables keyed by n (compact per-pass table) or -n (full table, t < n/2)
     mutable std::mutex mu;
     mutable std::map<int, swiftly::cplx*> tw;
+    // scratch lines of the split (2 x n/2) kernels, one buffer per stream: (pointer, samples)
+    mutable std::map<cudaStream_t, std::pair<swiftly::cplx*, size_t>> scratch;
     int force_split;  // debug / test: transform yN lines with the 2 x yN/2 split path
 };
 
@@ -30,6 +32,8 @@ int cuda_fail(cudaError_t e, const char* what);
 const cplx* twiddles(const swiftly_b200* h, int n);
 // full table exp(-2 pi i t / n), t < n / 2
 const cplx* twiddles_full(const swiftly_b200* h, int n);
+// per-stream scratch of at least `samples` complex samples (grown on demand)
+cplx* split_scratch(const swiftly_b200* h, cudaStream_t s, size_t samples);
 
 // largest directly supported power-of-two line length (fits shared memory)
 static const int MAX_DIRECT_FFT = 8192;
