@@ -44,6 +44,13 @@ METRIC = "facet->subgrid contributions/sec"
 UNIT = "contributions/s"
 
 
+def note(msg):
+    """Progress line on stderr (stdout carries only the JSON line)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+        sys.stderr.flush()
+
+
 def workload_params(name):
     from ska_sdp_distributed_fourier_transform_b200.swift_configs import SWIFT_CONFIGS
 
@@ -288,16 +295,21 @@ def main_gpu(args):
     from ska_sdp_distributed_fourier_transform_b200 import bench_support as bs
 
     params = workload_params(args.workload)
+    note(f"setting up {args.workload} on {world} GPU(s)")
     runner = bs.ForwardBenchRunner(params, dev, rank, world)
     hbm_gbs, peak_src = measured_peaks()
 
     # ---- device-resident runs (value) ----------------------------------------------
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         runner.step(timed=False)
+        note(f"warm-up step {i + 1}/{args.warmup} done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    times = [runner.step(timed=True) for _ in range(args.steps)]
+    times = []
+    for i in range(args.steps):
+        times.append(runner.step(timed=True))
+        note(f"timed step {i + 1}/{args.steps}: {times[-1]:.1f} ms")
     clocks = sampler.stop() if rank == 0 else None
     ms = float(numpy.mean(times))
     contributions = runner.contributions_per_step
@@ -306,12 +318,15 @@ def main_gpu(args):
     extra = {}
     if rank == 0 or world > 1:
         extra = runner.kernel_rooflines(hbm_gbs, step_ms=ms) if not args.no_roofline else {}
+    note("kernel rooflines done")
     e2e = None
     if not args.no_e2e:
-        e2e = runner.e2e(steps=args.e2e_steps)
+        e2e = runner.e2e(steps=args.e2e_steps, progress=note)
+        note(f"e2e done: {e2e['ms_per_step']:.1f} ms/step")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_entry(params, args.cpu_cores or (os.cpu_count() or 1))
+        note("cpu baseline done")
     if rank != 0:
         return
     line = {

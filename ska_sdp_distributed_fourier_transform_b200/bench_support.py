@@ -190,17 +190,19 @@ class ForwardBenchRunner:
         return {"kernels": kernels, "dominant": dominant, "bmin": bmin}
 
     # ------------------------------------------------------------------ end to end (host buffers)
-    def e2e(self, steps=1, ring=4):
+    def e2e(self, steps=1, ring=4, progress=None):
         """Same transform through the public API with HOST buffers: facets start in pinned
         host memory (H2D inside the timed region), every finished subgrid is copied to a
         pinned host buffer (D2H inside the timed region)."""
         yB, xA = self.yB, self.xA
         host = {}
         self.regenerate_facets()
-        for idx in self.local_idx:
+        for n, idx in enumerate(self.local_idx):
             h = torch.empty((yB, yB), dtype=torch.complex128, pin_memory=True)
             h.copy_(self.facet_views[idx])
             host[idx] = h
+            if progress is not None and n % 8 == 7:
+                progress(f"e2e: pinned {n + 1}/{len(self.local_idx)} host facets")
         slots = [torch.empty((xA, xA), dtype=torch.complex128, pin_memory=True)
                  for _ in range(ring)]
         d2h = torch.cuda.Stream(self.device)
@@ -228,6 +230,8 @@ class ForwardBenchRunner:
                 t = torch.tensor([dt], dtype=torch.float64, device=self.device)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
+            if progress is not None:
+                progress(f"e2e pass {it}: {dt * 1e3:.1f} ms")
             if it > 0:
                 times.append(dt)
         h2d = sum(h.numel() * 16 for h in host.values())
