@@ -57,6 +57,26 @@ def workload_params(name):
     return dict(SWIFT_CONFIGS[WORKLOADS[name]])
 
 
+def host_cores():
+    """CPU cores this process may actually use: min(affinity, cgroup quota, cpu_count).
+
+    The GPU boxes report 128 CPUs but run in a container limited to 16 CPUs / 200 GiB;
+    starting 128 numpy workers there exhausts the memory limit.
+    """
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -240,9 +260,7 @@ def main_reference(args):
     if rank != 0:
         return
     params = workload_params(args.workload)
-    cores = os.cpu_count() or 1
-    if args.cpu_cores:
-        cores = args.cpu_cores
+    cores = args.cpu_cores or host_cores()
     for _ in range(max(0, min(args.warmup, 1))):
         run_cpu_sample(params, cores, 1)
     t0 = time.perf_counter()
@@ -325,8 +343,13 @@ def main_gpu(args):
         note(f"e2e done: {e2e['ms_per_step']:.1f} ms/step")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_entry(params, args.cpu_cores or (os.cpu_count() or 1))
+        cpu = cpu_baseline_entry(params, args.cpu_cores or host_cores())
         note("cpu baseline done")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {
