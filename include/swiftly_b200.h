@@ -140,6 +140,19 @@ typedef struct swiftly_b200_source {
 int swiftly_b200_sum_finish_axis(const swiftly_b200* plan, const swiftly_b200_source* sources,
                                  int n_sources, const swiftly_b200_lines* out,
                                  int64_t subgrid_off, const double* mask, void* stream);
+/* The same for several independent source groups in ONE launch (e.g. all facet rows of a
+ * subgrid): group g takes sources [sum(group_sizes[:g]), ... + group_sizes[g]) and writes
+ * out->data + g * out_group_stride (complex elements); `out` describes one group's lines. */
+int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* plan,
+                                         const swiftly_b200_source* sources,
+                                         const int32_t* group_sizes, int n_groups,
+                                         const swiftly_b200_lines* out, int64_t out_group_stride,
+                                         int64_t subgrid_off, const double* mask, void* stream);
+/* swiftly_b200_extract_column for n_facets (<= 64) facets in ONE launch: bf_f[f] / out[f]
+ * as in swiftly_b200_extract_column (contiguous rows), facet_off1[f] per facet. */
+int swiftly_b200_extract_columns(const swiftly_b200* plan, int n_facets,
+                                 const swiftly_b200_lines* bf_f, const swiftly_b200_lines* out,
+                                 int64_t subgrid_off0, const int64_t* facet_off1, void* stream);
 /* xM_size / xM_yN_size if the fused kernel exists for this plan, else 0. */
 int swiftly_b200_sum_finish_axis_supported(const swiftly_b200* plan);
 

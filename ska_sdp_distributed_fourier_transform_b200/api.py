@@ -398,13 +398,12 @@ class SwiftlyForward:
             if len(self.lru.data) >= self.lru.size:
                 # recycle the buffers of the column that is about to be evicted
                 _, reuse = self.lru.data.popitem(last=False)
-            cached = []
-            for idx, ((cfg, _), BF_F) in enumerate(zip(self.facet_tasks, BF_Fs)):
-                buf = None if reuse is None else reuse[idx]
-                if self._fused:
-                    cached.append(self.core.extract_column(BF_F, off0, cfg.off1, out=buf))
-                else:
-                    cached.append(extract_column(self.core, BF_F, off0, cfg.off1))
+            if self._fused:
+                cached = self.core.extract_columns(
+                    BF_Fs, off0, [cfg.off1 for cfg, _ in self.facet_tasks], outs=reuse)
+            else:
+                cached = [extract_column(self.core, BF_F, off0, cfg.off1)
+                          for (cfg, _), BF_F in zip(self.facet_tasks, BF_Fs)]
             self.lru.set(off0, cached)
         return cached
 
@@ -423,11 +422,11 @@ class SwiftlyForward:
             self._strips = torch.empty(shape, dtype=torch.complex128, device=self.device)
         mask0 = _device_mask(sg.mask0, self.device)
         mask1 = _device_mask(sg.mask1, self.device)
-        for r, (_, members) in enumerate(self._rows):
-            core.sum_finish_axis(
-                [(NMBF_BFs[j], self.facet_tasks[j][0].off1) for j in members],
-                self._strips[r], axis=1, subgrid_off=sg.off1, mask=mask1,
-            )
+        core.sum_finish_axis_grouped(
+            [[(NMBF_BFs[j], self.facet_tasks[j][0].off1) for j in members]
+             for _, members in self._rows],
+            self._strips, axis=1, subgrid_off=sg.off1, mask=mask1,
+        )
         out = torch.empty((sg.size, sg.size), dtype=torch.complex128, device=self.device)
         core.sum_finish_axis(
             [(self._strips[r], off0) for r, (off0, _) in enumerate(self._rows)],

@@ -63,7 +63,9 @@ class ForwardBenchRunner:
         rows_local = len({self.facet_cfgs[i].off0 for i in self.local_idx})
         # launches of OUR kernels per step on this rank (stage 1, stage 2, axis-1, axis-0)
         owned_sg = len([i for i in range(len(self.sg_cfgs)) if i % world == rank])
-        self.launches_per_step = (F + ncols * F + len(self.sg_cfgs) * rows_local + owned_sg)
+        # stage 1 per facet; stage 2 one grouped launch per column (<= 64 facets each);
+        # axis 1 one grouped launch per subgrid; axis 0 one launch per owned subgrid
+        self.launches_per_step = (F + ncols * -(-F // 64) + len(self.sg_cfgs) + owned_sg)
         self._nrows = nrows
         self._gen = torch.Generator(device=device)
 
@@ -148,19 +150,28 @@ class ForwardBenchRunner:
         # make the row's BF_F valid for the following kernels
         for i in row_members:
             core.prepare_facet(self.facet_views[i], fcs[i].off0, axis=0, out=self.bf_views[i])
-        nmbf = {i: torch.empty((m, yN), dtype=torch.complex128, device=dev) for i in row_members}
-        t2 = self._time(lambda: core.extract_column(
-            self.bf_views[idx0], sg.off0, fcs[idx0].off1, out=nmbf[idx0]))
-        out["extract_column (Fb.FFT.extract, K2)"] = (t2, 16.0 * (m * yB + m * yN), ncols * F)
-        for i in row_members:
-            core.extract_column(self.bf_views[i], sg.off0, fcs[i].off1, out=nmbf[i])
+        # stage 2 exactly as the step launches it: all local facets of a column in one launch
+        for i in self.local_idx:
+            core.prepare_facet(self.facet_views[i], fcs[i].off0, axis=0, out=self.bf_views[i])
+        nmbf_all = [torch.empty((m, yN), dtype=torch.complex128, device=dev)
+                    for _ in self.local_idx]
+        bfs = [self.bf_views[i] for i in self.local_idx]
+        off1s = [fcs[i].off1 for i in self.local_idx]
+        t2 = self._time(lambda: core.extract_columns(bfs, sg.off0, off1s, outs=nmbf_all), 3)
+        out["extract_columns (Fb.FFT.extract, K2; all local facets of a column)"] = (
+            t2, 16.0 * (m * yB + m * yN) * F, ncols)
+        nmbf = dict(zip(self.local_idx, nmbf_all))
         nstrips = self._nrows
         strips = torch.empty((nstrips, m, xA), dtype=torch.complex128, device=dev)
-        srcs = [(nmbf[i], fcs[i].off1) for i in row_members]
-        t3 = self._time(lambda: core.sum_finish_axis(srcs, strips[0], axis=1, subgrid_off=sg.off1))
-        out["sum_finish_axis1 (per facet row)"] = (
-            t3, 16.0 * (nsrc * m * m + m * xA), S * rows_local)
-        for r in range(1, nstrips):
+        local_rows = sorted({fcs[i].off0 for i in self.local_idx})
+        groups = [[(nmbf[i], fcs[i].off1) for i in self.local_idx if fcs[i].off0 == o]
+                  for o in local_rows]
+        t3 = self._time(lambda: core.sum_finish_axis_grouped(
+            groups, strips[:len(groups)], axis=1, subgrid_off=sg.off1))
+        out["sum_finish_axis1 (all local facet rows of a subgrid)"] = (
+            t3, 16.0 * (F * m * m + len(groups) * m * xA), S)
+        srcs = groups[0]
+        for r in range(len(groups), nstrips):
             core.sum_finish_axis(srcs, strips[r], axis=1, subgrid_off=sg.off1)
         res = torch.empty((xA, xA), dtype=torch.complex128, device=dev)
         row_offs = sorted({c.off0 for c in fcs})

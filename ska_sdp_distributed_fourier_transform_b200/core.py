@@ -365,6 +365,75 @@ class SwiftlyCoreB200:
         _lib.check(self._lib, rc)
         return out
 
+    def extract_columns(self, BF_Fs, subgrid_off0, facet_off1s, outs=None):
+        """``extract_column`` for a list of facets in ONE kernel launch (<= 64 per launch)."""
+        shape = (self.xM_yN_size, self.yN_size)
+        BF_Fs = list(BF_Fs)
+        if outs is None:
+            outs = [None] * len(BF_Fs)
+        outs = [
+            torch.empty(shape, dtype=torch.complex128, device=b.device) if o is None else o
+            for b, o in zip(BF_Fs, outs)
+        ]
+        for lo in range(0, len(BF_Fs), 64):
+            chunk = range(lo, min(lo + 64, len(BF_Fs)))
+            din = (_lib.Lines * len(chunk))()
+            dout = (_lib.Lines * len(chunk))()
+            offs = (ctypes.c_int64 * len(chunk))()
+            for k, i in enumerate(chunk):
+                b, o = BF_Fs[i], outs[i]
+                self._check_tensor(b)
+                self._check_tensor(o)
+                if b.dtype != torch.complex128 or b.dim() != 2 or b.stride(1) != 1:
+                    raise ValueError("extract_columns needs row-contiguous complex128 tensors")
+                if tuple(o.shape) != shape or o.stride(1) != 1:
+                    raise ValueError(f"Output array has shape {tuple(o.shape)}, expected {shape}!")
+                din[k] = self._describe(b, 1)
+                dout[k] = self._describe(o, 1)
+                offs[k] = int(facet_off1s[i])
+            rc = self._lib.swiftly_b200_extract_columns(
+                self._plan, len(chunk), din, dout, int(subgrid_off0), offs,
+                self._stream(BF_Fs[lo]))
+            _lib.check(self._lib, rc)
+        return outs
+
+    def sum_finish_axis_grouped(self, groups, out, axis, subgrid_off, mask=None):
+        """:meth:`sum_finish_axis` for several source groups in ONE launch.
+
+        :param groups: list of source lists ``[(tensor, facet_off), ...]``
+        :param out: 3-D device tensor ``(n_groups, ...)``; ``out[g]`` receives group ``g``
+        """
+        if axis not in (0, 1):
+            raise ValueError(f"Invalid axis {axis}")
+        self._check_tensor(out)
+        if out.dim() != 3 or out.shape[0] != len(groups):
+            raise ValueError("out must be (n_groups, lines, size) / (n_groups, size, lines)")
+        flat = [s for grp in groups for s in grp]
+        arr = (_lib.Source * max(1, len(flat)))()
+        other = 1 - axis
+        for i, (t, facet_off) in enumerate(flat):
+            self._check_tensor(t)
+            if t.dtype != torch.complex128 or t.dim() != 2:
+                raise ValueError("sources must be 2-D complex128 device tensors")
+            if t.shape[other] != out.shape[1 + other]:
+                raise ValueError(
+                    f"source has {t.shape[other]} lines, output {out.shape[1 + other]}")
+            arr[i] = _lib.Source(t.data_ptr(), t.stride(other), t.stride(axis), t.shape[axis],
+                                 int(facet_off))
+        sizes = (ctypes.c_int32 * len(groups))(*[len(g) for g in groups])
+        dout = self._describe(out[0], axis)
+        mptr = ctypes.c_void_p(0)
+        if mask is not None:
+            if mask.dtype != torch.float64 or mask.numel() != out.shape[1 + axis]:
+                raise ValueError("mask must be float64 of the subgrid size")
+            mask = mask.contiguous()
+            mptr = ctypes.c_void_p(mask.data_ptr())
+        rc = self._lib.swiftly_b200_sum_finish_axis_grouped(
+            self._plan, arr, sizes, len(groups), ctypes.byref(dout), int(out.stride(0)),
+            int(subgrid_off), mptr, self._stream(out))
+        _lib.check(self._lib, rc)
+        return out
+
     def sum_finish_axis(self, sources, out, axis, subgrid_off, mask=None):
         """One axis of ``sum_and_finish_subgrid`` (api_helper.py:73-112) as ONE kernel.
 

@@ -47,12 +47,16 @@ extern "C" int swiftly_b200_sum_finish_axis_supported(const swiftly_b200* h) {
 }
 
 // Fused extract_from_facet + add_to_subgrid (summed over sources) + finish_subgrid along
-// one axis (SubgridAxisKernel, kernels.cuh).
-extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,
-                                            const swiftly_b200_source* sources, int n_sources,
-                                            const swiftly_b200_lines* out, int64_t subgrid_off,
-                                            const double* mask, void* stream) {
-    if (!h || !sources || !out) return einval("sum_finish_axis: NULL argument");
+// one axis (SubgridAxisKernel, kernels.cuh), for several independent source groups in one
+// launch: group g = sources [first_g, first_g + group_sizes[g]) -> out + g * out_group_stride.
+extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
+                                                    const swiftly_b200_source* sources,
+                                                    const int32_t* group_sizes, int n_groups,
+                                                    const swiftly_b200_lines* out,
+                                                    int64_t out_group_stride,
+                                                    int64_t subgrid_off, const double* mask,
+                                                    void* stream) {
+    if (!h || !sources || !out || !group_sizes) return einval("sum_finish_axis: NULL argument");
     if (out->location != SWIFTLY_B200_DEVICE) return einval("sum_finish_axis: device arrays only");
     const int64_t yN = h->yN, xM = h->xM, m = h->m;
     const int conc = subgrid_axis_conc((int)m, (int)xM);
@@ -61,37 +65,52 @@ extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,
                   ", xM=" + std::to_string(xM));
         return SWIFTLY_B200_EUNSUPPORTED;
     }
-    if (n_sources < 0) return einval("sum_finish_axis: negative source count");
+    if (n_groups < 1) return einval("sum_finish_axis: need at least one group");
     const int64_t sz = out->size;
     if (sz > xM) return einval("sum_finish_axis: subgrid size exceeds padded subgrid size");
     SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
 
-    // schedule sources into rounds of `conc` with pairwise disjoint accumulator windows
-    struct Win { int pos; };
-    std::vector<std::vector<int>> rounds;
-    std::vector<int> pos_of((size_t)n_sources);
-    for (int i = 0; i < n_sources; ++i) {
-        const swiftly_b200_source& sr = sources[i];
-        if (!sr.data) return einval("sum_finish_axis: NULL source pointer");
-        if (sr.size != yN && sr.size != m)
-            return einval("sum_finish_axis: source line length must be yN_size or xM_yN_size");
-        const int64_t sf = floordiv(sr.facet_off * xM, h->N);
-        pos_of[i] = (int)pmod(xM / 2 - m / 2 + sf, xM);
-        bool placed = false;
-        for (auto& r : rounds) {
-            if ((int)r.size() >= conc) continue;
-            bool clash = false;
-            for (int j : r) {
-                int64_t d1 = pmod(pos_of[j] - pos_of[i], xM), d2 = pmod(pos_of[i] - pos_of[j], xM);
-                if (d1 < m || d2 < m) { clash = true; break; }
+    // per group: schedule sources into rounds of `conc` with pairwise disjoint windows
+    std::vector<std::vector<std::vector<int>>> rounds((size_t)n_groups);
+    std::vector<int> pos_of;
+    int first = 0;
+    size_t max_rounds = 1;
+    for (int g = 0; g < n_groups; ++g) {
+        if (group_sizes[g] < 0) return einval("sum_finish_axis: negative group size");
+        for (int i = first; i < first + group_sizes[g]; ++i) {
+            const swiftly_b200_source& sr = sources[i];
+            if (!sr.data) return einval("sum_finish_axis: NULL source pointer");
+            if (sr.size != yN && sr.size != m)
+                return einval("sum_finish_axis: source line length must be yN_size or xM_yN_size");
+            const int64_t sf = floordiv(sr.facet_off * xM, h->N);
+            pos_of.push_back((int)pmod(xM / 2 - m / 2 + sf, xM));
+            bool placed = false;
+            for (auto& r : rounds[g]) {
+                if ((int)r.size() >= conc) continue;
+                bool clash = false;
+                for (int j : r) {
+                    int64_t d1 = pmod(pos_of[j] - pos_of[i], xM);
+                    int64_t d2 = pmod(pos_of[i] - pos_of[j], xM);
+                    if (d1 < m || d2 < m) {
+                        clash = true;
+                        break;
+                    }
+                }
+                if (!clash) {
+                    r.push_back(i);
+                    placed = true;
+                    break;
+                }
             }
-            if (!clash) { r.push_back(i); placed = true; break; }
+            if (!placed) rounds[g].push_back(std::vector<int>(1, i));
         }
-        if (!placed) rounds.push_back(std::vector<int>(1, i));
+        first += group_sizes[g];
+        if (rounds[g].size() > max_rounds) max_rounds = rounds[g].size();
     }
-    if ((int)rounds.size() * conc > SW_MAX_SOURCES)
+    const int slots = (int)max_rounds * conc;
+    if ((int64_t)slots * n_groups > SW_MAX_SOURCES)
         return einval("sum_finish_axis: too many sources for one launch (" +
-                      std::to_string(n_sources) + ")");
+                      std::to_string(first) + " in " + std::to_string(n_groups) + " groups)");
     SubgridAxisArgs a;
     for (int i = 0; i < SW_MAX_SOURCES; ++i) {
         a.src[i].base = nullptr;
@@ -100,35 +119,96 @@ extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,
         a.src[i].wmod = 1;
     }
     const int64_t sc = floordiv(subgrid_off * yN, h->N);
-    for (size_t r = 0; r < rounds.size(); ++r) {
-        for (size_t c = 0; c < rounds[r].size(); ++c) {
-            const int i = rounds[r][c];
-            const swiftly_b200_source& sr = sources[i];
-            SgSource& d = a.src[r * conc + c];
-            d.base = (const cplx*)sr.data;
-            d.ls = sr.line_stride;
-            d.es = sr.elem_stride;
-            if (sr.size == yN && yN != m) {  // window of a prepared facet line
-                d.wbase = (int)pmod(yN / 2 - m / 2 + sc, yN);
-                d.s_m = (int)pmod(sc, m);
-                d.wmod = (int)yN;
-            } else {  // already a contribution
-                d.wbase = 0;
-                d.s_m = 0;
-                d.wmod = (int)m;
+    for (int g = 0; g < n_groups; ++g) {
+        for (size_t r = 0; r < rounds[g].size(); ++r) {
+            for (size_t c = 0; c < rounds[g][r].size(); ++c) {
+                const int i = rounds[g][r][c];
+                const swiftly_b200_source& sr = sources[i];
+                SgSource& d = a.src[(size_t)g * slots + r * conc + c];
+                d.base = (const cplx*)sr.data;
+                d.ls = sr.line_stride;
+                d.es = sr.elem_stride;
+                if (sr.size == yN && yN != m) {  // window of a prepared facet line
+                    d.wbase = (int)pmod(yN / 2 - m / 2 + sc, yN);
+                    d.s_m = (int)pmod(sc, m);
+                    d.wmod = (int)yN;
+                } else {  // already a contribution
+                    d.wbase = 0;
+                    d.s_m = 0;
+                    d.wmod = (int)m;
+                }
+                const int64_t sf = floordiv(sr.facet_off * xM, h->N);
+                d.sf_m = (int)pmod(sf, m);
+                d.pos_base = pos_of[i];
             }
-            const int64_t sf = floordiv(sr.facet_off * xM, h->N);
-            d.sf_m = (int)pmod(sf, m);
-            d.pos_base = pos_of[i];
         }
     }
-    a.n_slots = (int)rounds.size() * conc;
+    a.n_slots = slots;
+    a.n_groups = n_groups;
     a.n_lines = out->n_lines;
     a.out = (cplx*)out->data;
     a.out_ls = out->line_stride;
     a.out_es = out->elem_stride;
+    a.out_gs = out_group_stride;
     a.sz = (int)sz;
     a.start = (int)pmod(xM / 2 - sz / 2 + subgrid_off, xM);
     a.mask = mask;
     return run_subgrid_axis(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,
+                                            const swiftly_b200_source* sources, int n_sources,
+                                            const swiftly_b200_lines* out, int64_t subgrid_off,
+                                            const double* mask, void* stream) {
+    if (n_sources < 0) return einval("sum_finish_axis: negative source count");
+    int32_t one = n_sources;
+    return swiftly_b200_sum_finish_axis_grouped(h, sources, &one, 1, out, 0, subgrid_off, mask,
+                                                stream);
+}
+
+// extract_column for several facets in one launch (same subgrid_off0; per-facet off1).
+extern "C" int swiftly_b200_extract_columns(const swiftly_b200* h, int n_facets,
+                                            const swiftly_b200_lines* bf_f,
+                                            const swiftly_b200_lines* out,
+                                            int64_t subgrid_off0, const int64_t* facet_off1,
+                                            void* stream) {
+    if (!h || !bf_f || !out || !facet_off1) return einval("extract_columns: NULL argument");
+    if (n_facets < 1 || n_facets > SW_MAX_COLUMN_FACETS)
+        return einval("extract_columns: between 1 and " + std::to_string(SW_MAX_COLUMN_FACETS) +
+                      " facets per call");
+    const int64_t yN = h->yN, m = h->m;
+    ExtractColumnsOp op;
+    for (int f = 0; f < n_facets; ++f) {
+        const swiftly_b200_lines& i = bf_f[f];
+        const swiftly_b200_lines& o = out[f];
+        if (i.location != SWIFTLY_B200_DEVICE || o.location != SWIFTLY_B200_DEVICE)
+            return einval("extract_columns: device arrays only");
+        if (i.n_lines != yN || i.elem_stride != 1 || o.elem_stride != 1)
+            return einval("extract_columns: prepared facets must be yN_size contiguous rows");
+        if (o.n_lines != m || o.size != yN)
+            return einval("extract_columns: output must be xM_yN_size lines of yN_size samples");
+        if (i.size > yN - 1) return einval("extract_columns: facet size must be at most yN_size - 1");
+        ColumnFacet& F = op.fac[f];
+        F.in = (const cplx*)i.data;
+        F.out = (cplx*)o.data;
+        F.in_ls = i.line_stride;
+        F.out_ls = o.line_stride;
+        F.fs = (int)i.size;
+        F.shift_in = (int)pmod(i.size / 2 - facet_off1[f], yN);
+        F.fb_off = (int)((yN - 1) / 2 - i.size / 2);
+        F.pad_ = 0;
+    }
+    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    const int64_t sc = floordiv(subgrid_off0 * yN, h->N);
+    op.g.in = nullptr;
+    op.g.out = nullptr;
+    op.g.in_ls = op.g.in_es = op.g.out_ls = op.g.out_es = 0;
+    op.g.n_lines = (int64_t)n_facets * m;
+    op.fb = h->d_Fb;
+    op.n = (int)yN;
+    op.lines_per = (int)m;
+    op.scale = 1.0 / (double)yN;
+    op.rm_s_m = (int)pmod(sc, m);
+    op.rm_base = (int)pmod(yN / 2 - m / 2 + sc, yN);
+    return run_extract_columns(h, op, false, (cudaStream_t)stream);
 }

@@ -1,0 +1,25 @@
+// SwiFTly B200 -- size dispatch of extract_columns (one translation unit per primitive keeps
+// the heavy FP64 template instantiations compiling in parallel).
+#include "dispatch.cuh"
+
+namespace swiftly {
+
+int run_extract_columns(const swiftly_b200* h, const ExtractColumnsOp& op, bool lf, cudaStream_t s) {
+    const int n = op.n;
+    if (h->force_split && n >= 2 * MIN_FFT && n <= MAX_DIRECT_FFT) {
+        switch (n) {
+#if defined(SWIFTLY_EMU)
+            case 128: return launch_split<64, +1, ExtractColumnsOp>(h, op, s);
+            case 512: return launch_split<256, +1, ExtractColumnsOp>(h, op, s);
+#endif
+            default: break;
+        }
+    }
+    switch (n) {
+        SW_DIRECT_CASES(+1, ExtractColumnsOp)
+        case 16384: return launch_split<8192, +1, ExtractColumnsOp>(h, op, s);
+        default: return unsupported(n);
+    }
+}
+
+}  // namespace swiftly

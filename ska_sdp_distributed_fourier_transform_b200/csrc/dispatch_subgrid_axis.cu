@@ -3,11 +3,12 @@
 
 namespace swiftly {
 
-template <int M, int XM>
-static int launch_sg_axis(const swiftly_b200* h, const SubgridAxisArgs& a, cudaStream_t s) {
-    SubgridAxisKernel<M, XM> k;
+template <int M, int XM, int LINES>
+static int launch_sg_axis_l(const swiftly_b200* h, const SubgridAxisArgs& a, cudaStream_t s) {
+    SubgridAxisKernel<M, XM, LINES> k;
     for (int i = 0; i < SW_MAX_SOURCES; ++i) k.src[i] = a.src[i];
     k.n_slots = a.n_slots;
+    k.n_groups = a.n_groups;
     k.fn = h->d_Fn;
     k.tw_m = twiddles(h, M);
     k.tw_x = twiddles(h, XM);
@@ -16,12 +17,27 @@ static int launch_sg_axis(const swiftly_b200* h, const SubgridAxisArgs& a, cudaS
     k.out = a.out;
     k.out_ls = a.out_ls;
     k.out_es = a.out_es;
+    k.out_gs = a.out_gs;
     k.sz = a.sz;
     k.start = a.start;
     k.scale = 1.0 / (double)XM;
     k.mask = a.mask;
-    cudaError_t e = launch_body(k, grid_for(a.n_lines, 1), k.SMEM, s);
+    cudaError_t e = launch_body(k, grid_for(((a.n_lines + LINES - 1) / LINES) * a.n_groups, 1), k.SMEM, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "subgrid axis kernel launch");
+}
+
+// two adjacent lines per CTA when every source and the output have unit line stride
+template <int M, int XM>
+static int launch_sg_axis(const swiftly_b200* h, const SubgridAxisArgs& a, cudaStream_t s) {
+    bool adjacent = a.out_ls == 1 && a.n_lines > 1;
+    for (int i = 0; i < SW_MAX_SOURCES && adjacent; ++i)
+        if (a.src[i].base && a.src[i].ls != 1) adjacent = false;
+    // 2 lines need 2 x (acc + work) of shared memory: only the pairs that fit
+    if constexpr (2 * ((size_t)(XM + 4) * sizeof(cplx) + (size_t)(XM + XM / 16 + 40) * 8) <=
+                  227 * 1024) {
+        if (adjacent) return launch_sg_axis_l<M, XM, 2>(h, a, s);
+    }
+    return launch_sg_axis_l<M, XM, 1>(h, a, s);
 }
 
 #define SW_SG_PAIRS(X) \

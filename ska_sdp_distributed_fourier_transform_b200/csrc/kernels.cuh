@@ -60,6 +60,43 @@ struct PrepareFacetOp {
     }
 };
 
+// Several prepare_facet jobs with a row map (extract_column of MANY facets, one launch):
+// global line L = f * lines_per + l belongs to facet f; per-facet base pointers / shifts
+// come from a table in the kernel parameters.
+struct ColumnFacet {
+    const cplx* in;   // BF_F of the facet (yN rows of fs samples)
+    cplx* out;        // NMBF_BF of the facet (m rows of yN samples)
+    int64_t in_ls, out_ls;
+    int fs, shift_in, fb_off;
+    int pad_;
+};
+#define SW_MAX_COLUMN_FACETS 64
+struct ExtractColumnsOp {
+    Lines g;           // only n_lines (= n_facets * lines_per) is used
+    ColumnFacet fac[SW_MAX_COLUMN_FACETS];
+    const double* fb;  // full Fb table
+    int n;             // yN
+    int lines_per;     // m
+    double scale;      // 1 / yN
+    int rm_s_m, rm_base;  // row map: input row = (rm_base + ((l - rm_s_m) mod m)) mod yN
+    SW_HD cplx load(int64_t line, int q) const {
+        const int f = (int)(line / lines_per);
+        const int l = (int)(line - (int64_t)f * lines_per);
+        const ColumnFacet& F = fac[f];
+        int k = wrap_add(q, F.shift_in, n);
+        if (k >= F.fs) return mk(0.0, 0.0);
+        int64_t row = wrap_add(rm_base, wrap_sub(l, rm_s_m, lines_per), n);
+        return cscale(ld_stream(F.in + row * F.in_ls + k), ldg_d(fb + F.fb_off + k));
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        const int f = (int)(line / lines_per);
+        const int l = (int)(line - (int64_t)f * lines_per);
+        const ColumnFacet& F = fac[f];
+        int pc = wrap_add(p, n / 2, n);
+        st_stream(F.out + (int64_t)l * F.out_ls + pc, cscale(v, scale));
+    }
+};
+
 // finish_facet (core.py:452-484): out[k] = Fb_c[k] * fft_c(sum)[(yN/2 - fs//2 + k + off) mod yN]
 struct FinishFacetOp {
     Lines g;
@@ -315,41 +352,61 @@ struct SgSource {
 };
 #define SW_MAX_SOURCES 64
 
-template <int M, int XM>
+// LINES = 2 processes two ADJACENT lines per CTA with the two lines interleaved across
+// lanes (lane pairs touch 32 contiguous bytes): used when lines are adjacent in memory
+// (axis-0 work on C-ordered arrays), where one line per CTA would fetch every 32-byte
+// sector twice.
+template <int M, int XM, int LINES>
 struct SubgridAxisKernel {
     static constexpr int T_M = FftCfg<M>::T;
-    static constexpr int THREADS = FftCfg<XM>::T;
-    static constexpr int CONC = THREADS / T_M;  // = XM / M concurrent m-point transforms
+    static constexpr int T_X = FftCfg<XM>::T;
+    static constexpr int THREADS = T_X * LINES;
+    static constexpr int CONC = T_X / T_M;  // = XM / M concurrent m-point transforms per line
     static constexpr int WSTRIDE = FftCfg<M>::PADDED | 1;
-    static constexpr int WORK = CONC * WSTRIDE;  // doubles, >= FftCfg<XM>::PADDED
-    static_assert(WORK >= FftCfg<XM>::PADDED, "work area must hold the xM exchange buffer");
-    static constexpr size_t SMEM = (size_t)XM * sizeof(cplx) + (size_t)WORK * sizeof(double);
+    static constexpr int WORK0 = CONC * WSTRIDE;  // doubles, >= FftCfg<XM>::PADDED
+    static_assert(WORK0 >= FftCfg<XM>::PADDED, "work area must hold the xM exchange buffer");
+    // per-line strides: the second line lands 8 bank pairs (64 B) away from the first
+    static constexpr int WORK = LINES == 1 ? WORK0 : ((WORK0 + 15) / 16) * 16 + 8;
+    static constexpr int ACCS = LINES == 1 ? XM : XM + 4;
+    static constexpr size_t SMEM =
+        ((size_t)ACCS * sizeof(cplx) + (size_t)WORK * sizeof(double)) * LINES;
 
+    // Several independent "groups" (e.g. the facet rows of one subgrid) share one launch:
+    // group g uses source slots [g * n_slots, (g + 1) * n_slots), has n_lines lines and
+    // writes to out + g * out_gs.
     SgSource src[SW_MAX_SOURCES];
-    int n_slots;
+    int n_slots;   // slots per group (multiple of CONC)
+    int n_groups;
     const double* fn;
     const cplx* tw_m;
     const cplx* tw_x;
-    int64_t n_lines;
+    int64_t n_lines;  // per group
     cplx* out;
-    int64_t out_ls, out_es;
+    int64_t out_ls, out_es, out_gs;
     int sz, start;
     double scale;        // 1 / xM
     const double* mask;  // sz doubles or null
 
     template <class Ctx>
     SW_HD void operator()(Ctx& ctx) const {
-        cplx* acc = (cplx*)ctx.smem;
-        double* work = (double*)(acc + XM);
-        const int c = ctx.tid / T_M;
-        const int lt = ctx.tid % T_M;
+        const int sub = ctx.tid % LINES;  // which of the CTA's lines
+        const int t = ctx.tid / LINES;    // thread within the line
+        cplx* acc = (cplx*)ctx.smem + (size_t)sub * ACCS;
+        double* work = (double*)((cplx*)ctx.smem + (size_t)LINES * ACCS) + (size_t)sub * WORK;
+        const int c = t / T_M;
+        const int lt = t % T_M;
         auto sync = [&]() { ctx.sync(); };
-        for (int64_t line = ctx.bid; line < n_lines; line += ctx.nblocks) {
-            for (int i = ctx.tid; i < XM; i += THREADS) acc[i] = mk(0.0, 0.0);
+        const int64_t lines_cta = (n_lines + LINES - 1) / LINES;  // line pairs per group
+        const int64_t total = lines_cta * n_groups;
+        for (int64_t gl = ctx.bid; gl < total; gl += ctx.nblocks) {
+            const int grp = (int)(gl / lines_cta);
+            const int64_t line = (gl - (int64_t)grp * lines_cta) * LINES + sub;
+            const bool line_ok = line < n_lines;
+            for (int i = t; i < XM; i += T_X) acc[i] = mk(0.0, 0.0);
             ctx.sync();
             for (int slot0 = 0; slot0 < n_slots; slot0 += CONC) {
-                const int slot = slot0 + c;
-                const bool active = slot < n_slots && src[slot].base != nullptr;
+                const int slot = grp * n_slots + slot0 + c;
+                const bool active = line_ok && slot0 + c < n_slots && src[slot].base != nullptr;
                 // keep the descriptor in registers (kernel parameters live in constant memory)
                 const cplx* base = active ? src[slot].base + line * src[slot].ls : nullptr;
                 const int64_t es = active ? src[slot].es : 0;
@@ -358,9 +415,9 @@ struct SubgridAxisKernel {
                 const int wmod = active ? src[slot].wmod : 1;
                 const int sf_m = active ? src[slot].sf_m : 0;
                 const int pos_base = active ? src[slot].pos_base : 0;
-                auto ld = [&](int t) {
+                auto ld = [&](int q) {
                     if (!active) return mk(0.0, 0.0);
-                    int tc = wrap_add(t, M / 2, M);
+                    int tc = wrap_add(q, M / 2, M);
                     int idx = wrap_add(wbase, wrap_sub(tc, s_m, M), wmod);
                     return ld_stream(base + (int64_t)idx * es);
                 };
@@ -377,17 +434,17 @@ struct SubgridAxisKernel {
                 ctx.sync();
             }
             {
-                cplx* o = out + line * out_ls;
+                cplx* o = out + (int64_t)grp * out_gs + line * out_ls;
                 auto ld = [&](int q) { return acc[wrap_add(q, XM / 2, XM)]; };
                 auto st = [&](int p, cplx v) {
                     int pc = wrap_add(p, XM / 2, XM);
                     int r = wrap_sub(pc, start, XM);
-                    if (r < sz) {
+                    if (line_ok && r < sz) {
                         double f = mask ? scale * ldg_d(mask + r) : scale;
                         st_stream(o + (int64_t)r * out_es, cscale(v, f));
                     }
                 };
-                line_fft<XM, +1>(ctx.tid, work, tw_x, ld, st, sync);
+                line_fft<XM, +1>(t, work, tw_x, ld, st, sync);
             }
             ctx.sync();  // acc / work are reused by the next line
         }

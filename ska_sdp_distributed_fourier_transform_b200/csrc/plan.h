@@ -48,14 +48,16 @@ int run_add_to_subgrid(const swiftly_b200* h, const AddToSubgridOp& op, bool lin
 int run_extract_from_subgrid(const swiftly_b200* h, const ExtractFromSubgridOp& op, bool line_fastest, cudaStream_t s);
 int run_finish_subgrid(const swiftly_b200* h, const FinishSubgridOp& op, bool line_fastest, cudaStream_t s);
 int run_prepare_subgrid(const swiftly_b200* h, const PrepareSubgridOp& op, bool line_fastest, cudaStream_t s);
+int run_extract_columns(const swiftly_b200* h, const ExtractColumnsOp& op, bool line_fastest, cudaStream_t s);
 
 // fused subgrid axis kernel (dispatch_subgrid_axis.cu); `k` carries everything but the tables
 struct SubgridAxisArgs {
     SgSource src[SW_MAX_SOURCES];
-    int n_slots;
-    int64_t n_lines;
+    int n_slots;   // per group
+    int n_groups;
+    int64_t n_lines;  // per group
     cplx* out;
-    int64_t out_ls, out_es;
+    int64_t out_ls, out_es, out_gs;
     int sz, start;
     const double* mask;
 };

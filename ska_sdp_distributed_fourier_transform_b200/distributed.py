@@ -106,12 +106,12 @@ class SwiftlyForwardSharded:
             reuse = None
             if len(self.lru.data) >= self.lru.size:
                 _, reuse = self.lru.data.popitem(last=False)
-            cached = {}
-            for i in self.local_idx:
-                buf = None if reuse is None else reuse[i]
-                cached[i] = self.core.extract_column(
-                    self.BF_Fs[i], off0, self.facet_configs[i].off1, out=buf)
-                self.launches += 1
+            outs = self.core.extract_columns(
+                [self.BF_Fs[i] for i in self.local_idx], off0,
+                [self.facet_configs[i].off1 for i in self.local_idx],
+                outs=None if reuse is None else [reuse[i] for i in self.local_idx])
+            cached = dict(zip(self.local_idx, outs))
+            self.launches += 1
             self.lru.set(off0, cached)
         return cached
 
@@ -129,11 +129,14 @@ class SwiftlyForwardSharded:
         """Axis-1 reduction of this rank's facets for subgrid ``sg`` into ``out[row]``."""
         column = self._column(sg.off0)
         mask1 = _device_mask(sg.mask1, self.device)
-        for r, off0 in enumerate(self.my_rows):
-            members = [i for i in self.local_idx if self.facet_configs[i].off0 == off0]
-            self.core.sum_finish_axis(
-                [(column[i], self.facet_configs[i].off1) for i in members],
-                out[r], axis=1, subgrid_off=sg.off1, mask=mask1)
+        groups = [
+            [(column[i], self.facet_configs[i].off1)
+             for i in self.local_idx if self.facet_configs[i].off0 == off0]
+            for off0 in self.my_rows
+        ]
+        if groups:
+            self.core.sum_finish_axis_grouped(
+                groups, out[:len(groups)], axis=1, subgrid_off=sg.off1, mask=mask1)
             self.launches += 1
 
     def _finish(self, sg, recv):
