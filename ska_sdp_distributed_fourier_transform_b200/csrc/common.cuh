@@ -81,6 +81,17 @@ SW_HD void st_stream(cplx* p, cplx v) {
 #endif
 }
 
+// software prefetch of the 32-byte sector(s) holding *p into L2 (no register is tied up):
+// all warps of a CTA are in the same phase of a transform, so a plain load at the start of
+// the next phase exposes the full DRAM latency; the prefetch is issued one phase ahead
+SW_HD void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // non-negative modulo for possibly negative a, n > 0
 SW_HD int64_t pmod(int64_t a, int64_t n) {
     int64_t r = a % n;
@@ -93,6 +104,10 @@ struct DeviceCtx {
     int tid, bid, nblocks;
     char* smem;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    // named barrier over `count` threads (a multiple of 32; whole warps), id 1..15
+    __device__ __forceinline__ void group_sync(int id, int count) const {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+    }
 };
 
 extern __shared__ __align__(16) char swiftly_dyn_smem[];

@@ -58,6 +58,13 @@ struct PrepareFacetOp {
         int pc = wrap_add(p, n / 2, n);
         st_stream(g.out + line * g.out_ls + (int64_t)pc * g.out_es, cscale(v, scale));
     }
+    SW_HD void prefetch(int64_t line, int q) const {
+        int k = wrap_add(q, shift_in, n);
+        if (k >= fs) return;
+        int64_t row = rm_m ? (int64_t)wrap_add(rm_base, wrap_sub((int)line, rm_s_m, rm_m), rm_mod)
+                           : line;
+        prefetch_l2(g.in + row * g.in_ls + (int64_t)k * g.in_es);
+    }
 };
 
 // Several prepare_facet jobs with a row map (extract_column of MANY facets, one launch):
@@ -95,6 +102,15 @@ struct ExtractColumnsOp {
         int pc = wrap_add(p, n / 2, n);
         st_stream(F.out + (int64_t)l * F.out_ls + pc, cscale(v, scale));
     }
+    SW_HD void prefetch(int64_t line, int q) const {
+        const int f = (int)(line / lines_per);
+        const int l = (int)(line - (int64_t)f * lines_per);
+        const ColumnFacet& F = fac[f];
+        int k = wrap_add(q, F.shift_in, n);
+        if (k >= F.fs) return;
+        int64_t row = wrap_add(rm_base, wrap_sub(l, rm_s_m, lines_per), n);
+        prefetch_l2(F.in + row * F.in_ls + k);
+    }
 };
 
 // finish_facet (core.py:452-484): out[k] = Fb_c[k] * fft_c(sum)[(yN/2 - fs//2 + k + off) mod yN]
@@ -107,6 +123,10 @@ struct FinishFacetOp {
     SW_HD cplx load(int64_t line, int q) const {
         int qc = wrap_add(q, n / 2, n);
         return ld_stream(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
+    }
+    SW_HD void prefetch(int64_t line, int q) const {
+        int qc = wrap_add(q, n / 2, n);
+        prefetch_l2(g.in + line * g.in_ls + (int64_t)qc * g.in_es);
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, n / 2, n);
@@ -271,6 +291,12 @@ struct SplitLineKernel {
                 line_fft<H, DIR>(lt, sm, tw, ld, st, sync);
             }
             ctx.sync();
+            if (line + ctx.nblocks < op.g.n_lines) {
+                // the O pass re-reads the sectors the E pass just fetched; use its time to pull
+                // the NEXT line of this CTA into L2
+#pragma unroll
+                for (int r = 0; r < 16; ++r) op.prefetch(line + ctx.nblocks, 2 * (lt + r * T));
+            }
             {
                 auto ld = [&](int q) { return op.load(line, 2 * q + 1); };
                 auto st = [&](int k, cplx o) {
@@ -396,6 +422,17 @@ struct SubgridAxisKernel {
         const int c = t / T_M;
         const int lt = t % T_M;
         auto sync = [&]() { ctx.sync(); };
+        // The CONC concurrent m-point transforms only need to synchronise among their own
+        // T_M * LINES threads: with one named barrier per transform the groups drift apart and
+        // the exchange phases (LSU bound) of some overlap the butterfly phases (FP64 bound) of
+        // others instead of the whole CTA alternating between the two.
+        constexpr bool GROUP_BARRIERS = (T_M * LINES) % 32 == 0 && CONC > 1 && CONC <= 15;
+        auto gsync = [&]() {
+            if (GROUP_BARRIERS)
+                ctx.group_sync(1 + c, T_M * LINES);
+            else
+                ctx.sync();
+        };
         const int64_t lines_cta = (n_lines + LINES - 1) / LINES;  // line pairs per group
         const int64_t total = lines_cta * n_groups;
         for (int64_t gl = ctx.bid; gl < total; gl += ctx.nblocks) {
@@ -430,7 +467,32 @@ struct SubgridAxisKernel {
                     cplx a = acc[pos];
                     acc[pos] = mk(a.x + f * v.x, a.y + f * v.y);
                 };
-                line_fft<M, -1>(lt, work + (size_t)c * WSTRIDE, tw_m, ld, st, sync);
+                // prefetch what this thread will load next into L2: the next round of this
+                // line, or -- in the last round -- the first round of the CTA's next line
+                {
+                    int pslot0 = slot0 + CONC, pgrp = grp;
+                    int64_t pline = line;
+                    if (pslot0 >= n_slots) {
+                        pslot0 = 0;
+                        const int64_t ngl = gl + ctx.nblocks;
+                        pgrp = (int)(ngl / lines_cta);
+                        pline = (ngl - (int64_t)pgrp * lines_cta) * LINES + sub;
+                        if (ngl >= total || pline >= n_lines) pgrp = -1;
+                    }
+                    if (pgrp >= 0 && pslot0 + c < n_slots) {
+                        const SgSource& ps = src[pgrp * n_slots + pslot0 + c];
+                        if (ps.base != nullptr) {
+                            const cplx* pb = ps.base + pline * ps.ls;
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                int tc = wrap_add(lt + r * T_M, M / 2, M);
+                                int idx = wrap_add(ps.wbase, wrap_sub(tc, ps.s_m, M), ps.wmod);
+                                prefetch_l2(pb + (int64_t)idx * ps.es);
+                            }
+                        }
+                    }
+                }
+                line_fft<M, -1>(lt, work + (size_t)c * WSTRIDE, tw_m, ld, st, gsync);
                 ctx.sync();
             }
             {

@@ -79,6 +79,9 @@ struct HostCtx {
     char* smem;
     EmuBlock* blk;
     inline void sync() const;
+    // named barriers: every group executes the same number of them in the kernels that use
+    // them, so a CTA-wide yield reproduces the semantics
+    inline void group_sync(int, int) const { sync(); }
 };
 
 struct EmuBlock {

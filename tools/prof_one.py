@@ -22,17 +22,18 @@ if which == "f1":
     for _ in range(reps):
         core.prepare_facet(facet, 0, axis=0, out=bf)
 elif which == "f2":
-    bf = torch.randn(yN, yB, dtype=torch.complex128, device=dev)
-    out = torch.empty(m, yN, dtype=torch.complex128, device=dev)
+    bfs = [torch.randn(yN, yB, dtype=torch.complex128, device=dev) for _ in range(nf)]
+    outs = [torch.empty(m, yN, dtype=torch.complex128, device=dev) for _ in range(nf)]
     for _ in range(reps):
-        core.extract_column(bf, 4096, 8192, out=out)
+        core.extract_columns(bfs, 4096, [yB * i for i in range(nf)], outs=outs)
 elif which in ("f3", "f4"):
     nmbf = [torch.randn(m, yN, dtype=torch.complex128, device=dev) for _ in range(nf)]
     strips = torch.randn(nf, m, xA, dtype=torch.complex128, device=dev)
     out = torch.empty(xA, xA, dtype=torch.complex128, device=dev)
     for _ in range(reps):
         if which == "f3":
-            core.sum_finish_axis([(nmbf[i], i * yB) for i in range(nf)], strips[0], axis=1, subgrid_off=2048)
+            core.sum_finish_axis_grouped([[(nmbf[i], i * yB) for i in range(nf)]] * nf, strips, axis=1,
+                                         subgrid_off=2048)
         else:
             core.sum_finish_axis([(strips[i], i * yB) for i in range(nf)], out, axis=0, subgrid_off=4096)
 torch.cuda.synchronize()
