@@ -291,12 +291,6 @@ struct SplitLineKernel {
                 line_fft<H, DIR>(lt, sm, tw, ld, st, sync);
             }
             ctx.sync();
-            if (line + ctx.nblocks < op.g.n_lines) {
-                // the O pass re-reads the sectors the E pass just fetched; use its time to pull
-                // the NEXT line of this CTA into L2
-#pragma unroll
-                for (int r = 0; r < 16; ++r) op.prefetch(line + ctx.nblocks, 2 * (lt + r * T));
-            }
             {
                 auto ld = [&](int q) { return op.load(line, 2 * q + 1); };
                 auto st = [&](int k, cplx o) {
@@ -479,7 +473,8 @@ struct SubgridAxisKernel {
                         pline = (ngl - (int64_t)pgrp * lines_cta) * LINES + sub;
                         if (ngl >= total || pline >= n_lines) pgrp = -1;
                     }
-                    if (pgrp >= 0 && pslot0 + c < n_slots) {
+                    // (measured: helps contiguous lines, hurts the strided two-line variant)
+                    if (LINES == 1 && pgrp >= 0 && pslot0 + c < n_slots) {
                         const SgSource& ps = src[pgrp * n_slots + pslot0 + c];
                         if (ps.base != nullptr) {
                             const cplx* pb = ps.base + pline * ps.ls;
