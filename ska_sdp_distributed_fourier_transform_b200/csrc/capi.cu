@@ -321,6 +321,40 @@ extern "C" int swiftly_b200_prepare_facet(const swiftly_b200* h, const swiftly_b
     const int64_t yN = h->yN, fs = in->size;
     // extract_mid(Fb, fs) needs fs <= len(Fb) = yN - 1 (core.py:213-215)
     if (fs > yN - 1) return einval("prepare_facet: facet size must be at most yN_size - 1");
+    // Strided axis with many adjacent lines: two-pass transform with coalesced column runs.
+    if (g.in_ls == 1 && g.out_ls == 1 && g.n_lines >= 16 && is_pow2(yN) && yN >= 256 &&
+        yN <= 65536 && !h->force_split) {
+        int lg = 0;
+        while (((int64_t)1 << lg) < yN) ++lg;
+        const int n1 = 1 << ((lg + 1) / 2), n2 = (int)(yN / n1);
+        const cplx* twf = twiddles_full(h, (int)yN);
+        cplx* scratch = split_scratch(h, s, (size_t)yN * (size_t)g.n_lines);
+        if (!twf || !scratch) return SWIFTLY_B200_ECUDA;
+        PrepareFacetPassAOp a;
+        a.g = g;
+        a.g.out = scratch;
+        a.g.n_lines = (int64_t)n2 * g.n_lines;
+        a.fb = h->d_Fb + ((yN - 1) / 2 - fs / 2);
+        a.twf = twf;
+        a.n = (int)yN;
+        a.n1 = n1;
+        a.n2 = n2;
+        a.fs = (int)fs;
+        a.shift_in = (int)pmod(fs / 2 - facet_off, yN);
+        a.ncols = (int)g.n_lines;
+        SW_TRY(run_prepare_facet_pass_a(h, a, s));
+        PrepareFacetPassBOp b;
+        b.g = g;
+        b.g.in = scratch;
+        b.g.n_lines = (int64_t)n1 * g.n_lines;
+        b.n = (int)yN;
+        b.n1 = n1;
+        b.n2 = n2;
+        b.ncols = (int)g.n_lines;
+        b.scale = 1.0 / (double)yN;
+        SW_TRY(run_prepare_facet_pass_b(h, b, s));
+        return stage_out(sout, s);
+    }
     PrepareFacetOp op;
     op.g = g;
     op.n = (int)yN;
@@ -329,6 +363,9 @@ extern "C" int swiftly_b200_prepare_facet(const swiftly_b200* h, const swiftly_b
     op.fb = h->d_Fb + ((yN - 1) / 2 - fs / 2);
     op.shift_in = (int)pmod(fs / 2 - facet_off, yN);
     op.scale = 1.0 / (double)yN;
+    op.rm_m = 0;
+    op.rm_s_m = op.rm_base = 0;
+    op.rm_mod = 1;
     SW_TRY(run_prepare_facet(h, op, lines_adjacent(g), s));
     return stage_out(sout, s);
 }

@@ -67,6 +67,57 @@ struct PrepareFacetOp {
     }
 };
 
+// prepare_facet along the STRIDED axis (axis 0 of a C-ordered facet) as a two-pass
+// ("four-step") transform so that every global access covers a run of adjacent columns:
+//   n = n1 * n2,  j = j1 n2 + j2,  k = k1 + n1 k2,  w = exp(+2 pi i / n)
+//   pass A (n1-point lines, one per (j2, column)):  T[k1 n2 + j2] = w^(j2 k1) sum_j1 z[j1 n2 + j2] w^(n2 j1 k1)
+//   pass B (n2-point lines, one per (k1, column)):  X[k1 + n1 k2] = sum_j2 T[k1 n2 + j2] w^(n1 j2 k2)
+// Line id = sub * ncols + column, and the line kernels run with LINE_FASTEST, so a warp touches
+// 16 adjacent columns (256 contiguous bytes) of one row per request.  The single-pass kernel
+// needs a whole 16384-point line per CTA and therefore one COLUMN per CTA: 16-byte accesses
+// at a 128 KiB stride, measured 2.6x DRAM write amplification (profiles/r01_ncu_f1_cfg4.txt).
+struct PrepareFacetPassAOp {
+    Lines g;  // g.in: facet (fs rows, ncols columns, row stride in_es); g.out: scratch T (n rows)
+    const double* fb;
+    const cplx* twf;  // exp(-2 pi i t / n), t < n/2
+    int n, n1, n2, fs, shift_in, ncols;
+    SW_HD cplx load(int64_t line, int q) const {
+        const int j2 = (int)(line / ncols);
+        const int c = (int)(line - (int64_t)j2 * ncols);
+        int k = wrap_add(q * n2 + j2, shift_in, n);
+        if (k >= fs) return mk(0.0, 0.0);
+        return cscale(ld_stream(g.in + (int64_t)k * g.in_es + c), ldg_d(fb + k));
+    }
+    SW_HD void store(int64_t line, int k1, cplx v) const {
+        const int j2 = (int)(line / ncols);
+        const int c = (int)(line - (int64_t)j2 * ncols);
+        int t = j2 * k1;  // < n
+        const bool neg = t >= n / 2;
+        if (neg) t -= n / 2;
+        cplx w = ldg_c(twf + t);
+        w.y = -w.y;  // inverse direction
+        cplx r = cmul(v, w);
+        if (neg) r = mk(-r.x, -r.y);
+        g.out[((int64_t)k1 * n2 + j2) * ncols + c] = r;
+    }
+};
+struct PrepareFacetPassBOp {
+    Lines g;  // g.in: scratch T; g.out: prepared facet (n rows, row stride out_es)
+    int n, n1, n2, ncols;
+    double scale;
+    SW_HD cplx load(int64_t line, int q) const {
+        const int k1 = (int)(line / ncols);
+        const int c = (int)(line - (int64_t)k1 * ncols);
+        return g.in[((int64_t)k1 * n2 + q) * ncols + c];
+    }
+    SW_HD void store(int64_t line, int k2, cplx v) const {
+        const int k1 = (int)(line / ncols);
+        const int c = (int)(line - (int64_t)k1 * ncols);
+        int pc = wrap_add(k1 + n1 * k2, n / 2, n);
+        st_stream(g.out + (int64_t)pc * g.out_es + c, cscale(v, scale));
+    }
+};
+
 // Several prepare_facet jobs with a row map (extract_column of MANY facets, one launch):
 // global line L = f * lines_per + l belongs to facet f; per-facet base pointers / shifts
 // come from a table in the kernel parameters.

@@ -88,3 +88,15 @@ def test_emu_golden_1d(emu_core_cls, golden_1d):
         pc.close(core.extract_from_subgrid(k("psg"), f_off, axis=0), k("ext"))
         assert numpy.array_equal(core.add_to_facet(k("ext"), s_off, axis=0), k("accf"))
         pc.close(core.finish_facet(k("accf"), f_off, yB, axis=0), k("fin"))
+
+
+@pytest.mark.parametrize("p,yB,cols", [(TESTP, 415, 37), (MID, 1500, 16), (TESTP, 416, 64)])
+def test_emu_prepare_facet_axis0_two_pass(emu_core_cls, p, yB, cols):
+    """Strided axis with >= 16 adjacent lines takes the two-pass (four-step) kernels."""
+    core, oracle = pc.make_pair(emu_core_cls, **p)
+    rng = numpy.random.default_rng(12)
+    Ny = core.facet_off_step
+    for f_off in (0, 5 * Ny, -11 * Ny):
+        facet = pc.rand_c(rng, yB, cols)
+        pc.close(core.prepare_facet(facet, f_off, axis=0),
+                 oracle.prepare_facet(facet, f_off, axis=0), what="two-pass prepare_facet")
