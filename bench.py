@@ -314,7 +314,7 @@ def main_gpu(args):
 
     params = workload_params(args.workload)
     note(f"setting up {args.workload} on {world} GPU(s)")
-    runner = bs.ForwardBenchRunner(params, dev, rank, world)
+    runner = bs.ForwardBenchRunner(params, dev, rank, world, exchange=args.exchange)
     hbm_gbs, peak_src = measured_peaks()
 
     # ---- device-resident runs (value) ----------------------------------------------
@@ -360,6 +360,8 @@ def main_gpu(args):
         "step_ms": times, "gpu_launches": runner.launches_per_step,
         "clocks": clocks,
     }
+    if world > 1:
+        line["config"]["exchange"] = runner.exchange_used
     if extra:
         line["roofline"] = extra["dominant"]
         line["roofline"]["peak_source"] = peak_src
@@ -384,6 +386,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU strip exchange: peer-memory stores or NCCL all_to_all")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

@@ -27,7 +27,9 @@ class ForwardBenchRunner:
     """Synthetic full-cover forward transform of one parameter set on ``world`` GPUs."""
 
     # pylint: disable=too-many-instance-attributes
-    def __init__(self, params, device, rank=0, world=1):
+    def __init__(self, params, device, rank=0, world=1, exchange="auto"):
+        self.exchange = exchange
+        self.exchange_used = None
         self.params = dict(params)
         self.device = device
         self.rank = rank
@@ -89,7 +91,8 @@ class ForwardBenchRunner:
                     consumer(i, sg, task.tensor)
             return
         fwd = SwiftlyForwardSharded(self.cfg, self.facet_cfgs, facet_data, lru_forward=1,
-                                    bf_f_buffers=self.bf_views)
+                                    bf_f_buffers=self.bf_views, exchange=self.exchange)
+        self.exchange_used = fwd.exchange
         fwd.get_subgrid_tasks(self.sg_cfgs, consumer=consumer or (lambda *a: None))
 
     def _barrier(self):

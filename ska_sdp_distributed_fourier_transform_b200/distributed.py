@@ -17,6 +17,19 @@ move and without replicating the axis-0 work.  The exchange of batch ``k`` runs 
 the communication stream while the compute stream produces the strips of batch
 ``k + 1`` and finishes the subgrids of batch ``k - 1``.
 
+Two exchange mechanisms:
+
+* ``exchange="p2p"`` (default when the ranks share an NVLink domain): the receive buffers are
+  allocated as *symmetric memory* (``torch.distributed._symmetric_memory``), every rank maps
+  its peers' buffers, and the axis-1 kernel of subgrid ``b`` stores its strips DIRECTLY into
+  the owner's buffer over NVLink -- the transfer is the kernel's own epilogue, tile by tile,
+  there is no separate collective and no staging copy.  One device-side barrier per batch
+  orders "all strips written" before the owners' axis-0 kernels; with two buffer slots the
+  same barrier also protects the re-use of a slot two batches later.
+* ``exchange="nccl"``: strips are written locally and moved by one ``all_to_all`` per batch
+  on the communication stream, overlapped with the compute stream (double buffered).  This
+  is also the path the CPU (gloo) tests exercise.
+
 Calls are collective (SPMD): every rank must call ``get_subgrid_tasks`` with the same
 subgrid list.
 """
@@ -58,7 +71,7 @@ class SwiftlyForwardSharded:
 
     # pylint: disable=too-many-instance-attributes,too-many-arguments
     def __init__(self, swiftly_config, facet_configs, local_facets, lru_forward=1, group=None,
-                 bf_f_buffers=None):
+                 bf_f_buffers=None, exchange="auto"):
         self.config = swiftly_config
         self.core = swiftly_config.core
         self.device = _device_of(self.core)
@@ -85,6 +98,52 @@ class SwiftlyForwardSharded:
         self.my_rows = self.rank_rows[self.rank]
         self._bufs = {}
         self.launches = 0
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"unknown exchange mechanism {exchange!r}")
+        self.exchange = "nccl"
+        self._symm = None
+        if exchange in ("auto", "p2p") and self.world > 1 and self.device.type == "cuda":
+            try:
+                self._setup_symmetric()
+                self.exchange = "p2p"
+            except Exception as exc:  # pylint: disable=broad-except
+                if exchange == "p2p":
+                    raise
+                self._symm = None
+                self.exchange_fallback_reason = f"{type(exc).__name__}: {exc}"
+        elif exchange == "p2p" and self.world == 1:
+            self.exchange = "nccl"
+
+    # ------------------------------------------------------------------ symmetric memory
+    def _setup_symmetric(self):
+        """Allocate the receive slots as symmetric memory and map every peer's copy."""
+        import torch.distributed._symmetric_memory as symm_mem  # pylint: disable=import-outside-toplevel
+
+        grp = self.group if self.group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(grp.group_name)
+        except Exception:  # pylint: disable=broad-except
+            pass  # newer torch enables it lazily
+        self._symm = {"mod": symm_mem, "group": grp, "slots": {}}
+
+    def _symm_slots(self, xA):
+        """(handle, [per-rank views of both slots]) for subgrid size ``xA``."""
+        st = self._symm
+        if xA not in st["slots"]:
+            m = self.core.xM_yN_size
+            shape = (2, self.world, self.rows_max, m, xA)
+            n = 1
+            for d in shape:
+                n *= d
+            buf = st["mod"].empty(2 * n, dtype=torch.float64, device=self.device)
+            buf.zero_()
+            hdl = st["mod"].rendezvous(buf, group=st["group"])
+            views = []
+            for r in range(self.world):
+                peer = hdl.get_buffer(r, (2 * n,), torch.float64, 0)
+                views.append(torch.view_as_complex(peer.view(n, 2)).view(shape))
+            st["slots"][xA] = (hdl, views, buf)
+        return st["slots"][xA]
 
     # ------------------------------------------------------------------ local stages
     def _prepare(self):
@@ -170,6 +229,8 @@ class SwiftlyForwardSharded:
         xA = sizes.pop()
         batches = [subgrid_configs[i:i + self.world]
                    for i in range(0, len(subgrid_configs), self.world)]
+        if self.exchange == "p2p":
+            return self._run_p2p(batches, xA, consumer, results)
         pending = None  # (batch index, work, recv buffer)
 
         def finish(bi, work, recv):
@@ -200,4 +261,23 @@ class SwiftlyForwardSharded:
                 finish(*pending)
             pending = (bi, work, recv)
         finish(*pending)
+        return results
+
+    def _run_p2p(self, batches, xA, consumer, results):
+        """Strips go straight into the owners' symmetric buffers (NVLink stores from the
+        axis-1 kernel); one device-side barrier per batch."""
+        hdl, views, _ = self._symm_slots(xA)
+        for bi, batch in enumerate(batches):
+            slot = bi % 2
+            for b, sg in enumerate(batch):
+                # owner of this subgrid is rank b: write my strips into ITS slot, at my index
+                self._local_strips(sg, views[b][slot, self.rank])
+            hdl.barrier(channel=slot)
+            if self.rank < len(batch):
+                idx = bi * self.world + self.rank
+                out = self._finish(batch[self.rank], views[self.rank][slot])
+                if consumer is not None:
+                    consumer(idx, batch[self.rank], out)
+                else:
+                    results[idx] = DeviceTask(out)
         return results

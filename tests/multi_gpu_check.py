@@ -31,10 +31,13 @@ def main():
         SwiftlyForwardSharded, partition_facets)
 
     worst_all = 0.0
-    for name, (W, N, yB, yN, xA, xM), sparse in (
-        ("cfg1", (13.5625, 1024, 416, 512, 228, 256), False),
-        ("n2048", (13.5625, 2048, 512, 1024, 256, 512), False),
-        ("n2048-sparse", (13.5625, 2048, 512, 1024, 256, 512), True),
+    for name, (W, N, yB, yN, xA, xM), sparse, exchange in (
+        ("cfg1", (13.5625, 1024, 416, 512, 228, 256), False, "nccl"),
+        ("cfg1-p2p", (13.5625, 1024, 416, 512, 228, 256), False, "p2p"),
+        ("n2048", (13.5625, 2048, 512, 1024, 256, 512), False, "nccl"),
+        ("n2048-p2p", (13.5625, 2048, 512, 1024, 256, 512), False, "p2p"),
+        ("n2048-sparse-p2p", (13.5625, 2048, 512, 1024, 256, 512), True, "p2p"),
+        ("n2048-sparse", (13.5625, 2048, 512, 1024, 256, 512), True, "nccl"),
     ):
         cfg = SwiftlyConfig(W=W, fov=1.0, N=N, yB_size=yB, yN_size=yN, xA_size=xA, xM_size=xM,
                             device=local)
@@ -47,7 +50,8 @@ def main():
                   for _ in facet_cfgs]
         owner = partition_facets(facet_cfgs, world)
         local_facets = {i: facets[i] for i, o in enumerate(owner) if o == rank}
-        fwd = SwiftlyForwardSharded(cfg, facet_cfgs, local_facets, lru_forward=1)
+        fwd = SwiftlyForwardSharded(cfg, facet_cfgs, local_facets, lru_forward=1,
+                                    exchange=exchange)
         sgs = make_full_subgrid_cover(cfg)
         sgs = sgs[:2 * world + 1] + sgs[-3:]
         tasks = fwd.get_subgrid_tasks(sgs)
@@ -63,7 +67,7 @@ def main():
         t = torch.tensor([worst], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"{name}: world={world} max rel err {t.item():.2e}")
+            print(f"{name}: world={world} exchange={fwd.exchange} max rel err {t.item():.2e}")
         worst_all = max(worst_all, t.item())
     dist.destroy_process_group()
     assert worst_all <= 1e-9, worst_all
