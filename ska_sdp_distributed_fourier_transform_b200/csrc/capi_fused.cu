@@ -143,6 +143,11 @@ extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
             }
         }
     }
+    // does the first round of every group tile the accumulator (conc disjoint windows of m
+    // samples with conc * m == xM)?  Then it may store instead of accumulate.
+    a.first_round_tiles = ((int64_t)conc * m == xM) ? 1 : 0;
+    for (int g = 0; g < n_groups && a.first_round_tiles; ++g)
+        if (rounds[g].empty() || (int)rounds[g][0].size() != conc) a.first_round_tiles = 0;
     a.n_slots = slots;
     a.n_groups = n_groups;
     a.n_lines = out->n_lines;

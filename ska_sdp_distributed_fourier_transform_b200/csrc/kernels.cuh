@@ -457,6 +457,10 @@ struct SubgridAxisKernel {
     int sz, start;
     double scale;        // 1 / xM
     const double* mask;  // sz doubles or null
+    // set by the host when, in EVERY group, the windows of the first round are pairwise
+    // disjoint and tile the accumulator completely (the regular facet layouts): the first
+    // round then stores instead of read-modify-write and the accumulator is not zeroed
+    int first_round_tiles;
 
     template <class Ctx>
     SW_HD void operator()(Ctx& ctx) const {
@@ -484,9 +488,12 @@ struct SubgridAxisKernel {
             const int grp = (int)(gl / lines_cta);
             const int64_t line = (gl - (int64_t)grp * lines_cta) * LINES + sub;
             const bool line_ok = line < n_lines;
-            for (int i = t; i < XM; i += T_X) acc[i] = mk(0.0, 0.0);
-            ctx.sync();
+            if (!first_round_tiles) {
+                for (int i = t; i < XM; i += T_X) acc[i] = mk(0.0, 0.0);
+                ctx.sync();
+            }
             for (int slot0 = 0; slot0 < n_slots; slot0 += CONC) {
+                const bool overwrite = first_round_tiles && slot0 == 0;
                 const int slot = grp * n_slots + slot0 + c;
                 const bool active = line_ok && slot0 + c < n_slots && src[slot].base != nullptr;
                 // keep the descriptor in registers (kernel parameters live in constant memory)
@@ -509,8 +516,12 @@ struct SubgridAxisKernel {
                     int u = wrap_sub(wc, sf_m, M);
                     int pos = wrap_add(pos_base, u, XM);
                     double f = ldg_d(fn + u);
-                    cplx a = acc[pos];
-                    acc[pos] = mk(a.x + f * v.x, a.y + f * v.y);
+                    if (overwrite) {
+                        acc[pos] = mk(f * v.x, f * v.y);
+                    } else {
+                        cplx a = acc[pos];
+                        acc[pos] = mk(a.x + f * v.x, a.y + f * v.y);
+                    }
                 };
                 // prefetch what this thread will load next into L2: the next round of this
                 // line, or -- in the last round -- the first round of the CTA's next line

@@ -62,6 +62,7 @@ struct SubgridAxisArgs {
     int64_t out_ls, out_es, out_gs;
     int sz, start;
     const double* mask;
+    int first_round_tiles;
 };
 // returns SWIFTLY_B200_EUNSUPPORTED (without setting up anything) when the (m, xM) pair has no
 // fused instantiation; conc_out receives the number of sources processed concurrently

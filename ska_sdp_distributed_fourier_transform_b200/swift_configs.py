@@ -1,15 +1,22 @@
 """
-Named SwiFTly parameter sets.
+Named SwiFTly parameter sets (``SWIFT_CONFIGS[name]`` -> ``SwiftlyConfig`` keyword dict).
 
-The reference ships a catalogue of 244 entries (``swift_configs.py``); entries are plain
-``SwiftlyConfig`` keyword dictionaries.  This module carries the parameter sets the
-BASELINE benchmark is quoted on (none of which is in the reference catalogue, see
-SURVEY.md section 8d) plus the reference's unit-test set; any dictionary with the same keys --
-including every entry of the reference catalogue whose FFT lengths are powers of two --
-can be passed to ``SwiftlyConfig(**params)``.
+* the four BASELINE benchmark sets (none of which is in the reference catalogue, SURVEY.md
+  section 8d) and the reference's unit-test set;
+* the reference's own catalogue (244 entries, ``swift_configs.py`` there), carried as a data
+  table ``swift_configs.json`` exported by ``tools/make_catalogue.py`` -- same names, same
+  keys (``W, fov, N, Nx, yB_size, yN_size, yP_size, xA_size, xM_size``).
+
+``runnable(params)`` tells whether this build can transform a set: the kernels of this round
+need power-of-two FFT lengths (``yN_size``, ``xM_size``, ``xM_size*yN_size/N``), 16...16384;
+catalogue families with factors 3, 5, 7 construct (parameter checks, window tables) but raise
+``NotImplementedError`` when a transform is requested.
 """
 
-SWIFT_CONFIGS = {
+import json
+import os
+
+_BASELINE = {
     # reference tests/test_core.py:20-27, tests/test_api.py:32-40
     "1k[1]-n512-256": dict(W=13.5625, fov=1.0, N=1024, yB_size=416, yN_size=512,
                            xA_size=228, xM_size=256),
@@ -21,3 +28,26 @@ SWIFT_CONFIGS = {
     "64k[1]-n16k-4k": dict(W=13.5625, fov=1.0, N=65536, yB_size=8192, yN_size=16384,
                            xA_size=2048, xM_size=4096),
 }
+
+
+def _load_catalogue():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "swift_configs.json")
+    out = {}
+    if os.path.exists(path):
+        with open(path) as f:
+            table = json.load(f)
+        cols = table["columns"][1:]
+        for row in table["rows"]:
+            out[row[0]] = {k: v for k, v in zip(cols, row[1:]) if v is not None}
+    return out
+
+
+SWIFT_CONFIGS = _load_catalogue()
+SWIFT_CONFIGS.update(_BASELINE)
+
+
+def runnable(params):
+    """True if every FFT length of the parameter set is a power of two in 16...16384."""
+    N, yN, xM = params["N"], params["yN_size"], params["xM_size"]
+    sizes = (yN, xM, xM * yN // N)
+    return all(16 <= s <= 16384 and s & (s - 1) == 0 for s in sizes) and xM <= 8192

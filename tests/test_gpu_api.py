@@ -75,3 +75,32 @@ def test_cfg2_forward_vs_oracle_and_dft():
     for sg in (sg_cfgs[0], sg_cfgs[9], sg_cfgs[-1]):
         err = check_subgrid(N, sg, fwd.get_subgrid_task(sg).tensor, sources)
         assert err < 1e-13, err
+
+
+def test_catalogue_config_round_trip():
+    """A runnable entry of the reference catalogue through the full API (forward vs analytic
+    DFT, backward vs the source list), and a non-power-of-two entry failing loudly."""
+    from ska_sdp_distributed_fourier_transform_b200 import (
+        SWIFT_CONFIGS, SwiftlyBackward, check_facet)
+    from ska_sdp_distributed_fourier_transform_b200.swift_configs import runnable
+
+    name = "4k[1]-n2k-512"
+    params = SWIFT_CONFIGS[name]
+    assert runnable(params)
+    cfg = SwiftlyConfig(**params)
+    N = cfg.image_size
+    sources = [(1, 1, 0), (0.5, -200, 333)]
+    facet_cfgs = make_full_facet_cover(cfg)
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    fwd = SwiftlyForward(cfg, [(fc, make_facet(N, fc, sources)) for fc in facet_cfgs])
+    bwd = SwiftlyBackward(cfg, facet_cfgs)
+    for sg in sg_cfgs:
+        task = fwd.get_subgrid_task(sg)
+        assert check_subgrid(N, sg, task.tensor, sources) < 1e-12
+        bwd.add_new_subgrid_task(sg, task)
+    for fc, task in zip(facet_cfgs, bwd.finish()):
+        assert check_facet(N, fc, task.result(), sources) < 1e-8
+    odd = next(c for c in SWIFT_CONFIGS.values() if not runnable(c) and c["N"] <= 4096)
+    cfg_odd = SwiftlyConfig(**odd)
+    with pytest.raises(NotImplementedError):
+        cfg_odd.core.prepare_facet(numpy.zeros(odd["yB_size"]), 0, axis=0)
