@@ -8,8 +8,15 @@ int run_add_to_subgrid(const swiftly_b200* h, const AddToSubgridOp& op, bool lf,
     const int n = op.m;
     switch (n) {
         SW_DIRECT_CASES(-1, AddToSubgridOp)
-        default: return unsupported(n);
+        default: break;
     }
+    {
+        int M = 0, F = 0;
+        if (split_f_plan(n, &M, &F)) {
+            SW_SPLIT_F_CASES(-1, AddToSubgridOp, M, F)
+        }
+    }
+    return unsupported(n);
 }
 
 }  // namespace swiftly

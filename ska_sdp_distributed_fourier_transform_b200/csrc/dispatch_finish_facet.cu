@@ -18,8 +18,15 @@ int run_finish_facet(const swiftly_b200* h, const FinishFacetOp& op, bool lf, cu
     switch (n) {
         SW_DIRECT_CASES(-1, FinishFacetOp)
         case 16384: return launch_split<8192, -1, FinishFacetOp>(h, op, s);
-        default: return unsupported(n);
+        default: break;
     }
+    {
+        int M = 0, F = 0;
+        if (split_f_plan(n, &M, &F)) {
+            SW_SPLIT_F_CASES(-1, FinishFacetOp, M, F)
+        }
+    }
+    return unsupported(n);
 }
 
 }  // namespace swiftly

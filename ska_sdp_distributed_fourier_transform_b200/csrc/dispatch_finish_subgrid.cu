@@ -8,8 +8,15 @@ int run_finish_subgrid(const swiftly_b200* h, const FinishSubgridOp& op, bool lf
     const int n = op.xM;
     switch (n) {
         SW_DIRECT_CASES(+1, FinishSubgridOp)
-        default: return unsupported(n);
+        default: break;
     }
+    {
+        int M = 0, F = 0;
+        if (split_f_plan(n, &M, &F)) {
+            SW_SPLIT_F_CASES(+1, FinishSubgridOp, M, F)
+        }
+    }
+    return unsupported(n);
 }
 
 }  // namespace swiftly

@@ -8,8 +8,15 @@ int run_prepare_subgrid(const swiftly_b200* h, const PrepareSubgridOp& op, bool 
     const int n = op.xM;
     switch (n) {
         SW_DIRECT_CASES(-1, PrepareSubgridOp)
-        default: return unsupported(n);
+        default: break;
     }
+    {
+        int M = 0, F = 0;
+        if (split_f_plan(n, &M, &F)) {
+            SW_SPLIT_F_CASES(-1, PrepareSubgridOp, M, F)
+        }
+    }
+    return unsupported(n);
 }
 
 }  // namespace swiftly

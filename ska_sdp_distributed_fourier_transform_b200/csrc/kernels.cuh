@@ -359,6 +359,73 @@ struct SplitLineKernel {
     }
 };
 
+// N = F * M point transform for ANY small factor F <= 16 and power-of-two M (non power-of-two
+// lengths of the parameter catalogue: yN, xM = {3, 5, 7, 9} * 2^k, and lengths above 16384):
+// decimation in time by F,
+//   E_q = FFT_M(z[F j + q]),  X[k + M s] = sum_q (w^(q k) E_q[k]) exp(DIR 2 pi i q s / F),
+//   w = exp(DIR 2 pi i / N).
+// E_0 .. E_{F-2} are parked in the per-CTA scratch (L2), E_{F-1} stays in registers; the
+// combine is a dense F-point DFT per output index (F^2 complex multiplies per F outputs --
+// these lengths are off the benchmark path, generality over speed).
+// twf: exp(-2 pi i t / N), t < N/2 (N is even for every SwiFTly size); wf: exp(-2 pi i t / F).
+#define SW_MAX_SPLIT_F 16
+template <int M, int DIR, class Op>
+struct SplitFKernel {
+    static constexpr int T = FftCfg<M>::T;
+    static constexpr int THREADS = T;
+    static constexpr size_t SMEM = (size_t)FftCfg<M>::PADDED * sizeof(double);
+    Op op;
+    const cplx* tw;   // compact table of the M-point plan
+    const cplx* twf;  // exp(-2 pi i t / N), t < N / 2
+    cplx* scratch;    // gridDim.x * (F - 1) * M samples
+    int F;
+    cplx wf[SW_MAX_SPLIT_F];  // exp(-2 pi i t / F)
+
+    SW_HD cplx root_n(int64_t t, int64_t n) const {  // exp(DIR 2 pi i t / n), 0 <= t < n
+        const bool neg = t >= n / 2;
+        cplx w = ldg_c(twf + (neg ? t - n / 2 : t));
+        if (DIR > 0) w.y = -w.y;
+        return neg ? mk(-w.x, -w.y) : w;
+    }
+
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        double* sm = (double*)ctx.smem;
+        cplx* stash = scratch + (size_t)ctx.bid * (size_t)(F - 1) * M;
+        const int lt = ctx.tid;
+        const int64_t n = (int64_t)F * M;
+        auto sync = [&]() { ctx.sync(); };
+        for (int64_t line = ctx.bid; line < op.g.n_lines; line += ctx.nblocks) {
+            for (int q = 0; q < F; ++q) {
+                auto ld = [&](int j) { return op.load(line, F * j + q); };
+                if (q < F - 1) {
+                    cplx* sq = stash + (size_t)q * M;
+                    auto st = [&](int k, cplx v) { sq[k] = v; };
+                    line_fft<M, DIR>(lt, sm, tw, ld, st, sync);
+                } else {
+                    auto st = [&](int k, cplx last) {
+                        cplx e[SW_MAX_SPLIT_F];
+                        for (int qq = 0; qq < F - 1; ++qq)
+                            e[qq] = cmul(stash[(size_t)qq * M + k], root_n((int64_t)qq * k, n));
+                        e[F - 1] = cmul(last, root_n((int64_t)(F - 1) * k, n));
+                        for (int s = 0; s < F; ++s) {
+                            cplx acc = e[0];
+                            for (int qq = 1; qq < F; ++qq) {
+                                cplx w = wf[(qq * s) % F];
+                                if (DIR > 0) w.y = -w.y;
+                                acc = cadd(acc, cmul(e[qq], w));
+                            }
+                            op.store(line, k + M * s, acc);
+                        }
+                    };
+                    line_fft<M, DIR>(lt, sm, tw, ld, st, sync);
+                }
+                ctx.sync();
+            }
+        }
+    }
+};
+
 // ------------------------------------------------------------------ gather / scatter kernels
 // extract_from_facet (core.py:224-253):  out[t] = prep[(base + ((t - s_m) mod m)) mod yN]
 // add_to_facet      (core.py:408-449):  out[(base + ((t - s_m) mod m)) mod yN] += contrib[t]

@@ -7,9 +7,11 @@ Named SwiFTly parameter sets (``SWIFT_CONFIGS[name]`` -> ``SwiftlyConfig`` keywo
   table ``swift_configs.json`` exported by ``tools/make_catalogue.py`` -- same names, same
   keys (``W, fov, N, Nx, yB_size, yN_size, yP_size, xA_size, xM_size``).
 
-``runnable(params)`` tells whether this build can transform a set: the kernels of this round
-need power-of-two FFT lengths (``yN_size``, ``xM_size``, ``xM_size*yN_size/N``), 16...16384;
-catalogue families with factors 3, 5, 7 construct (parameter checks, window tables) but raise
+``runnable(params)`` tells whether this build can transform a set: every FFT length
+(``yN_size``, ``xM_size``, ``xM_size*yN_size/N``) must be ``F * 2^k`` with ``F <= 16`` and
+``16 <= 2^k <= 8192`` -- true for all 244 catalogue entries (factors 3, 5, 7, 9 and lengths up
+to 65536 go through the generic split-F kernel; the fused forward kernels cover the
+power-of-two sets, the others run primitive by primitive on the GPU).  Anything else raises
 ``NotImplementedError`` when a transform is requested.
 """
 
@@ -46,8 +48,25 @@ SWIFT_CONFIGS = _load_catalogue()
 SWIFT_CONFIGS.update(_BASELINE)
 
 
+def fft_length_supported(n):
+    """``n = F * 2^k`` with ``F <= 16`` and ``16 <= 2^k <= 8192`` (or a power of two <= 16384)."""
+    if n < 16 or n % 2:
+        return False
+    m = 1
+    while n % (2 * m) == 0 and 2 * m <= 8192:
+        m *= 2
+    return m >= 16 and n // m <= 16
+
+
 def runnable(params):
-    """True if every FFT length of the parameter set is a power of two in 16...16384."""
+    """True if this build has kernels for every FFT length of the parameter set."""
     N, yN, xM = params["N"], params["yN_size"], params["xM_size"]
-    sizes = (yN, xM, xM * yN // N)
-    return all(16 <= s <= 16384 and s & (s - 1) == 0 for s in sizes) and xM <= 8192
+    return all(fft_length_supported(s) for s in (yN, xM, xM * yN // N))
+
+
+def fused_forward(params):
+    """True if the fused forward kernels (power-of-two m, xM with xM/m in {2, 4}) apply."""
+    N, yN, xM = params["N"], params["yN_size"], params["xM_size"]
+    m = xM * yN // N
+    pow2 = lambda v: v & (v - 1) == 0  # noqa: E731
+    return pow2(m) and pow2(xM) and xM // m in (2, 4) and 32 <= m <= 2048 and xM <= 8192

