@@ -145,3 +145,27 @@ def test_golden_2d(core_cls, golden_2d):
     Nx = core.subgrid_off_step
     pc.close(core.finish_subgrid(g["fs_in"], [2 * Nx, -Nx], xA - 1), g["fs_out"])
     pc.close(core.prepare_subgrid(g["ps_in"], (2 * Nx, -Nx)), g["ps_out"])
+
+
+NONPOW2 = [
+    dict(W=11.0, N=1536, xM=512, yN=768),
+    dict(W=9.25, N=1792, xM=256, yN=1792),
+    dict(W=11.0, N=1280, xM=320, yN=640),
+    dict(W=11.0, N=2304, xM=576, yN=1152),
+    dict(W=11.0, N=114688, xM=512, yN=57344),   # catalogue 112k[1]-n56k-512: yN = 7 * 8192
+]
+
+
+@pytest.mark.parametrize("p", NONPOW2)
+def test_non_power_of_two_lengths(core_cls, p):
+    """F * 2^k FFT lengths (F = 3, 5, 7, 9) through the generic split-F kernel."""
+    core, oracle = pc.make_pair(core_cls, **p)
+    rng = numpy.random.default_rng(13)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    yB = (p["yN"] * 11 // 16) | 1
+    xA = (p["xM"] * 7 // 8) & ~1
+    pc.check_1d_chain(core, oracle, yB, xA, 3 * Ny, -5 * Nx, rng)
+    pc.check_1d_chain(core, oracle, yB - 1, xA - 1, -2 * Ny, 4 * Nx, rng)
+    if p["yN"] < 4096:
+        pc.check_2d_axis(core, oracle, yB, 0, 17, Ny, -Nx, rng)
+        pc.check_2d_axis(core, oracle, yB, 1, 5, Ny, -Nx, rng)
