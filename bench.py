@@ -77,6 +77,24 @@ def host_cores():
     return max(1, n)
 
 
+def measured_traffic(kernel_name, world):
+    """DRAM bytes per launch of the named kernel from the committed ncu capture (N=1 only)."""
+    if world != 1:
+        return None
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                table = json.load(f)
+        except (OSError, ValueError):
+            continue
+        for key, val in table.items():
+            if not key.startswith("_") and key in kernel_name:
+                return val["dram_bytes_per_launch"]
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -365,6 +383,8 @@ def main_gpu(args):
     if extra:
         line["roofline"] = extra["dominant"]
         line["roofline"]["peak_source"] = peak_src
+        if args.workload == "cfg4":
+            line["roofline"]["traffic"] = measured_traffic(line["roofline"]["kernel"], world)
         line["kernel_rooflines"] = extra["kernels"]
         line["bmin_roofline"] = extra["bmin"]
     if e2e is not None:
