@@ -116,3 +116,47 @@ def test_catalogue_config_round_trip():
     bad = SwiftlyCoreB200(11.0, 544, 272, 272)
     with pytest.raises(NotImplementedError):
         bad.prepare_facet(numpy.zeros(100), 0, axis=0)
+
+
+def test_cfg4_full_size_properties():
+    """BASELINE cfg4 geometry (N=65536, yN=16384 split kernels, m=1024, xM=4096) at full
+    size through the fused pipeline: (1) point sources inside two facets -> the subgrids equal
+    the analytic DFT (all other facets are empty, so the two-facet sum is the exact answer);
+    (2) linearity of the whole transform on dense random facets."""
+    W, N, yB, yN, xA, xM = 13.5625, 65536, 8192, 16384, 2048, 4096
+    cfg = make_config(W, N, yB, yN, xA, xM)
+    rng = numpy.random.default_rng(65536)
+    fcs = [FacetConfig(0, 8192, yB), FacetConfig(57344, 8192, yB)]  # rows 0 and 7, column 1
+    sources = []
+    for fc in fcs:
+        for _ in range(6):
+            l = (fc.off0 + int(rng.integers(-yB // 2, yB // 2)) + N // 2) % N - N // 2
+            m_ = (fc.off1 + int(rng.integers(-yB // 2, yB // 2)) + N // 2) % N - N // 2
+            sources.append((float(rng.random()) + 0.5, l, m_))
+    facets = [make_facet(N, fc, sources) for fc in fcs]
+    assert abs(sum(f.sum() for f in facets) - sum(s[0] for s in sources)) < 1e-9
+    fwd = SwiftlyForward(cfg, list(zip(fcs, facets)))
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    for sg in (sg_cfgs[0], sg_cfgs[33], sg_cfgs[-1]):
+        got = fwd.get_subgrid_task(sg).tensor
+        err = check_subgrid(N, sg, got, sources)
+        scale = sum(s[0] for s in sources) / N**2  # magnitude of the subgrid samples
+        assert err / scale < 1e-9, (err, scale)
+    del fwd
+    torch.cuda.empty_cache()
+    # linearity
+    a, b = 0.75, -1.25 + 0.5j
+    F1 = [pc.rand_c(rng, yB, yB) for _ in fcs]
+    F2 = [pc.rand_c(rng, yB, yB) for _ in fcs]
+    sg = sg_cfgs[40]
+
+    def run(data):
+        f = SwiftlyForward(cfg, list(zip(fcs, data)))
+        out = f.get_subgrid_task(sg).tensor.clone()
+        del f
+        return out
+
+    s1, s2 = run(F1), run(F2)
+    s12 = run([a * x + b * y for x, y in zip(F1, F2)])
+    ref = a * s1 + b * s2
+    assert float((s12 - ref).abs().max() / ref.abs().max()) < 1e-12
