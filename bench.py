@@ -327,6 +327,10 @@ def main_gpu(args):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL prints its version banner on STDOUT (NCCL_DEBUG=VERSION in this image); stdout
+        # must carry the JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from ska_sdp_distributed_fourier_transform_b200 import bench_support as bs
 
