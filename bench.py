@@ -315,6 +315,23 @@ def workload_config(name, params, gpus):
 
 # ====================================================================== GPU arm
 def main_gpu(args):
+    # Everything but the final JSON line goes to stderr -- also what libraries print on the C
+    # level (NCCL writes its version banner to stdout when the first communicator is created).
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _main_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line))
+        sys.stdout.flush()
+
+
+def _main_gpu(args):
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -373,7 +390,7 @@ def main_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
-        return
+        return None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -395,7 +412,7 @@ def main_gpu(args):
         line["e2e"] = e2e
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    return line
 
 
 def main():
