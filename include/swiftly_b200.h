@@ -148,6 +148,14 @@ int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* plan,
                                          const int32_t* group_sizes, int n_groups,
                                          const swiftly_b200_lines* out, int64_t out_group_stride,
                                          int64_t subgrid_off, const double* mask, void* stream);
+/* As above, but the groups may belong to different subgrids (a batch of the multi-GPU
+ * driver): subgrid_offs[g] and masks[g] (masks or masks[g] may be NULL) per group; <= 16 groups. */
+int swiftly_b200_sum_finish_axis_batched(const swiftly_b200* plan,
+                                         const swiftly_b200_source* sources,
+                                         const int32_t* group_sizes, int n_groups,
+                                         const swiftly_b200_lines* out, int64_t out_group_stride,
+                                         const int64_t* subgrid_offs, const double* const* masks,
+                                         void* stream);
 /* swiftly_b200_extract_column for n_facets (<= 64) facets in ONE launch: bf_f[f] / out[f]
  * as in swiftly_b200_extract_column (contiguous rows), facet_off1[f] per facet. */
 int swiftly_b200_extract_columns(const swiftly_b200* plan, int n_facets,

@@ -67,7 +67,9 @@ class ForwardBenchRunner:
         owned_sg = len([i for i in range(len(self.sg_cfgs)) if i % world == rank])
         # stage 1 per facet; stage 2 one grouped launch per column (<= 64 facets each);
         # axis 1 one grouped launch per subgrid; axis 0 one launch per owned subgrid
-        self.launches_per_step = (F + ncols * -(-F // 64) + len(self.sg_cfgs) + owned_sg)
+        # (multi-GPU: the axis-1 launch covers a whole batch of world subgrids)
+        axis1 = len(self.sg_cfgs) if world == 1 else -(-len(self.sg_cfgs) // world)
+        self.launches_per_step = (F + ncols * -(-F // 64) + axis1 + owned_sg)
         self._nrows = nrows
         self._gen = torch.Generator(device=device)
 

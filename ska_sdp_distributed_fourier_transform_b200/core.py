@@ -402,7 +402,12 @@ class SwiftlyCoreB200:
 
         :param groups: list of source lists ``[(tensor, facet_off), ...]``
         :param out: 3-D device tensor ``(n_groups, ...)``; ``out[g]`` receives group ``g``
+        :param subgrid_off: one offset, or a list with one offset per group (groups of
+            different subgrids, e.g. a batch of the multi-GPU driver)
+        :param mask: one mask (or None), or a list with one mask / None per group
         """
+        if isinstance(subgrid_off, (list, tuple)):
+            return self._sum_finish_axis_batched(groups, out, axis, subgrid_off, mask)
         if axis not in (0, 1):
             raise ValueError(f"Invalid axis {axis}")
         self._check_tensor(out)
@@ -431,6 +436,46 @@ class SwiftlyCoreB200:
         rc = self._lib.swiftly_b200_sum_finish_axis_grouped(
             self._plan, arr, sizes, len(groups), ctypes.byref(dout), int(out.stride(0)),
             int(subgrid_off), mptr, self._stream(out))
+        _lib.check(self._lib, rc)
+        return out
+
+    def _sum_finish_axis_batched(self, groups, out, axis, subgrid_offs, masks):
+        if axis not in (0, 1):
+            raise ValueError(f"Invalid axis {axis}")
+        self._check_tensor(out)
+        if out.dim() != 3 or out.shape[0] != len(groups) or len(subgrid_offs) != len(groups):
+            raise ValueError("out / subgrid_off must have one entry per group")
+        if masks is None:
+            masks = [None] * len(groups)
+        flat = [s for grp in groups for s in grp]
+        arr = (_lib.Source * max(1, len(flat)))()
+        other = 1 - axis
+        for i, (t, facet_off) in enumerate(flat):
+            self._check_tensor(t)
+            if t.dtype != torch.complex128 or t.dim() != 2:
+                raise ValueError("sources must be 2-D complex128 device tensors")
+            if t.shape[other] != out.shape[1 + other]:
+                raise ValueError(
+                    f"source has {t.shape[other]} lines, output {out.shape[1 + other]}")
+            arr[i] = _lib.Source(t.data_ptr(), t.stride(other), t.stride(axis), t.shape[axis],
+                                 int(facet_off))
+        sizes = (ctypes.c_int32 * len(groups))(*[len(g) for g in groups])
+        offs = (ctypes.c_int64 * len(groups))(*[int(o) for o in subgrid_offs])
+        keep = []
+        mptrs = (ctypes.c_void_p * len(groups))()
+        for g, mk in enumerate(masks):
+            if mk is None:
+                mptrs[g] = None
+            else:
+                if mk.dtype != torch.float64 or mk.numel() != out.shape[1 + axis]:
+                    raise ValueError("mask must be float64 of the subgrid size")
+                mk = mk.contiguous()
+                keep.append(mk)
+                mptrs[g] = mk.data_ptr()
+        dout = self._describe(out[0], axis)
+        rc = self._lib.swiftly_b200_sum_finish_axis_batched(
+            self._plan, arr, sizes, len(groups), ctypes.byref(dout), int(out.stride(0)),
+            offs, mptrs, self._stream(out))
         _lib.check(self._lib, rc)
         return out
 

@@ -49,14 +49,14 @@ extern "C" int swiftly_b200_sum_finish_axis_supported(const swiftly_b200* h) {
 // Fused extract_from_facet + add_to_subgrid (summed over sources) + finish_subgrid along
 // one axis (SubgridAxisKernel, kernels.cuh), for several independent source groups in one
 // launch: group g = sources [first_g, first_g + group_sizes[g]) -> out + g * out_group_stride.
-extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
-                                                    const swiftly_b200_source* sources,
-                                                    const int32_t* group_sizes, int n_groups,
-                                                    const swiftly_b200_lines* out,
-                                                    int64_t out_group_stride,
-                                                    int64_t subgrid_off, const double* mask,
-                                                    void* stream) {
+static int sum_finish_groups(const swiftly_b200* h, const swiftly_b200_source* sources,
+                             const int32_t* group_sizes, int n_groups,
+                             const swiftly_b200_lines* out, int64_t out_group_stride,
+                             const int64_t* subgrid_offs, const double* const* masks,
+                             void* stream) {
     if (!h || !sources || !out || !group_sizes) return einval("sum_finish_axis: NULL argument");
+    if (n_groups > SW_MAX_GROUPS)
+        return einval("sum_finish_axis: at most " + std::to_string(SW_MAX_GROUPS) + " groups");
     if (out->location != SWIFTLY_B200_DEVICE) return einval("sum_finish_axis: device arrays only");
     const int64_t yN = h->yN, xM = h->xM, m = h->m;
     const int conc = subgrid_axis_conc((int)m, (int)xM);
@@ -118,8 +118,8 @@ extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
         a.src[i].wbase = a.src[i].s_m = a.src[i].sf_m = a.src[i].pos_base = 0;
         a.src[i].wmod = 1;
     }
-    const int64_t sc = floordiv(subgrid_off * yN, h->N);
     for (int g = 0; g < n_groups; ++g) {
+        const int64_t sc = floordiv(subgrid_offs[g] * yN, h->N);
         for (size_t r = 0; r < rounds[g].size(); ++r) {
             for (size_t c = 0; c < rounds[g][r].size(); ++c) {
                 const int i = rounds[g][r][c];
@@ -156,9 +156,45 @@ extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
     a.out_es = out->elem_stride;
     a.out_gs = out_group_stride;
     a.sz = (int)sz;
-    a.start = (int)pmod(xM / 2 - sz / 2 + subgrid_off, xM);
-    a.mask = mask;
+    for (int g = 0; g < SW_MAX_GROUPS; ++g) {
+        const int gg = g < n_groups ? g : 0;
+        a.start[g] = (int)pmod(xM / 2 - sz / 2 + subgrid_offs[gg], xM);
+        a.mask[g] = masks ? masks[gg] : nullptr;
+    }
     return run_subgrid_axis(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
+                                                    const swiftly_b200_source* sources,
+                                                    const int32_t* group_sizes, int n_groups,
+                                                    const swiftly_b200_lines* out,
+                                                    int64_t out_group_stride,
+                                                    int64_t subgrid_off, const double* mask,
+                                                    void* stream) {
+    if (n_groups < 1 || n_groups > SW_MAX_GROUPS)
+        return einval("sum_finish_axis: between 1 and " + std::to_string(SW_MAX_GROUPS) + " groups");
+    int64_t offs[SW_MAX_GROUPS];
+    const double* masks[SW_MAX_GROUPS];
+    for (int g = 0; g < n_groups; ++g) {
+        offs[g] = subgrid_off;
+        masks[g] = mask;
+    }
+    return sum_finish_groups(h, sources, group_sizes, n_groups, out, out_group_stride, offs, masks,
+                             stream);
+}
+
+// Groups that belong to DIFFERENT subgrids (a batch of the multi-GPU driver): per-group
+// subgrid offset and mask.
+extern "C" int swiftly_b200_sum_finish_axis_batched(const swiftly_b200* h,
+                                                    const swiftly_b200_source* sources,
+                                                    const int32_t* group_sizes, int n_groups,
+                                                    const swiftly_b200_lines* out,
+                                                    int64_t out_group_stride,
+                                                    const int64_t* subgrid_offs,
+                                                    const double* const* masks, void* stream) {
+    if (!subgrid_offs) return einval("sum_finish_axis: NULL subgrid offsets");
+    return sum_finish_groups(h, sources, group_sizes, n_groups, out, out_group_stride,
+                             subgrid_offs, masks, stream);
 }
 
 extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,

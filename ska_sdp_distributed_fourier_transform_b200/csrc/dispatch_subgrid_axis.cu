@@ -19,9 +19,11 @@ static int launch_sg_axis_l(const swiftly_b200* h, const SubgridAxisArgs& a, cud
     k.out_es = a.out_es;
     k.out_gs = a.out_gs;
     k.sz = a.sz;
-    k.start = a.start;
+    for (int g = 0; g < SW_MAX_GROUPS; ++g) {
+        k.start[g] = a.start[g];
+        k.mask[g] = a.mask[g];
+    }
     k.scale = 1.0 / (double)XM;
-    k.mask = a.mask;
     k.first_round_tiles = a.first_round_tiles;
     cudaError_t e = launch_body(k, grid_for(((a.n_lines + LINES - 1) / LINES) * a.n_groups, 1), k.SMEM, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "subgrid axis kernel launch");

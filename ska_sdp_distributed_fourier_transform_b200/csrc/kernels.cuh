@@ -489,6 +489,7 @@ struct SgSource {
     int sf_m, pos_base;    // sf mod m ; (xM/2 - m/2 + sf) mod xM
 };
 #define SW_MAX_SOURCES 64
+#define SW_MAX_GROUPS 16
 
 // LINES = 2 processes two ADJACENT lines per CTA with the two lines interleaved across
 // lanes (lane pairs touch 32 contiguous bytes): used when lines are adjacent in memory
@@ -521,9 +522,10 @@ struct SubgridAxisKernel {
     int64_t n_lines;  // per group
     cplx* out;
     int64_t out_ls, out_es, out_gs;
-    int sz, start;
-    double scale;        // 1 / xM
-    const double* mask;  // sz doubles or null
+    int sz;
+    int start[SW_MAX_GROUPS];           // per group: (xM/2 - sz//2 + subgrid_off) mod xM
+    const double* mask[SW_MAX_GROUPS];  // per group: sz doubles or null
+    double scale;                       // 1 / xM
     // set by the host when, in EVERY group, the windows of the first round are pairwise
     // disjoint and tile the accumulator completely (the regular facet layouts): the first
     // round then stores instead of read-modify-write and the accumulator is not zeroed
@@ -621,12 +623,14 @@ struct SubgridAxisKernel {
             }
             {
                 cplx* o = out + (int64_t)grp * out_gs + line * out_ls;
+                const int gstart = start[grp];
+                const double* gmask = mask[grp];
                 auto ld = [&](int q) { return acc[wrap_add(q, XM / 2, XM)]; };
                 auto st = [&](int p, cplx v) {
                     int pc = wrap_add(p, XM / 2, XM);
-                    int r = wrap_sub(pc, start, XM);
+                    int r = wrap_sub(pc, gstart, XM);
                     if (line_ok && r < sz) {
-                        double f = mask ? scale * ldg_d(mask + r) : scale;
+                        double f = gmask ? scale * ldg_d(gmask + r) : scale;
                         st_stream(o + (int64_t)r * out_es, cscale(v, f));
                     }
                 };

@@ -60,8 +60,9 @@ struct SubgridAxisArgs {
     int64_t n_lines;  // per group
     cplx* out;
     int64_t out_ls, out_es, out_gs;
-    int sz, start;
-    const double* mask;
+    int sz;
+    int start[SW_MAX_GROUPS];
+    const double* mask[SW_MAX_GROUPS];
     int first_round_tiles;
 };
 // returns SWIFTLY_B200_EUNSUPPORTED (without setting up anything) when the (m, xM) pair has no

@@ -202,6 +202,46 @@ class SwiftlyForwardSharded:
                 groups, out[:len(groups)], axis=1, subgrid_off=sg.off1, mask=mask1)
             self.launches += 1
 
+    def _local_strips_batch(self, batch, out):
+        """Axis-1 reduction for all subgrids of a batch: ``out[b, row]`` for subgrid ``b``.
+
+        Subgrids that share the subgrid column (``off0``) go into ONE kernel launch (groups =
+        subgrids x local facet rows, per-group subgrid offset and mask)."""
+        max_groups = 16
+        b = 0
+        while b < len(batch):
+            e = b
+            while (e < len(batch) and batch[e].off0 == batch[b].off0
+                   and (e - b + 1) * max(1, len(self.my_rows)) <= max_groups
+                   and batch[e].size == batch[b].size):
+                e += 1
+            if not self.my_rows:
+                b = e
+                continue
+            run = batch[b:e]
+            nrows = len(self.my_rows)
+            if out[b:e, :nrows].stride(0) != out[b:e, :nrows].stride(1) * nrows:
+                # strips of consecutive subgrids are not evenly spaced (padded rows): per subgrid
+                for k, sg in enumerate(run):
+                    self._local_strips(sg, out[b + k])
+                b = e
+                continue
+            column = self._column(run[0].off0)
+            groups, offs, masks = [], [], []
+            for sg in run:
+                mask1 = _device_mask(sg.mask1, self.device)
+                for off0 in self.my_rows:
+                    groups.append([(column[i], self.facet_configs[i].off1)
+                                   for i in self.local_idx
+                                   if self.facet_configs[i].off0 == off0])
+                    offs.append(sg.off1)
+                    masks.append(mask1)
+            m, xA = out.shape[-2], out.shape[-1]
+            view = out[b:e, :nrows].reshape(len(run) * nrows, m, xA)
+            self.core.sum_finish_axis_grouped(groups, view, axis=1, subgrid_off=offs, mask=masks)
+            self.launches += 1
+            b = e
+
     def _finish(self, sg, recv):
         """Axis-0 reduction over the strips of all ranks (owner only)."""
         sources = []
@@ -251,8 +291,7 @@ class SwiftlyForwardSharded:
 
         for bi, batch in enumerate(batches):
             send, recv = self._buffers(bi % 2, xA)
-            for b, sg in enumerate(batch):
-                self._local_strips(sg, send[b])
+            self._local_strips_batch(batch, send)
             work = None
             if self.world > 1:
                 work = dist.all_to_all_single(
