@@ -161,6 +161,25 @@ int swiftly_b200_sum_finish_axis_batched(const swiftly_b200* plan,
 int swiftly_b200_extract_columns(const swiftly_b200* plan, int n_facets,
                                  const swiftly_b200_lines* bf_f, const swiftly_b200_lines* out,
                                  int64_t subgrid_off0, const int64_t* facet_off1, void* stream);
+/* ---- fused backward path (device memory only) --------------------------------------- */
+/* One subgrid into the column accumulators of n_facets (<= 64) facets in ONE launch: per
+ * facet `extract_from_subgrid(block, facet_off1, axis=1)` followed by `accumulate_column` =
+ * `add_to_facet(., subgrid_off1, axis=1, out=acc)` (api_helper.py:115-152).  blocks[f]: the
+ * (xM_yN_size x xM_size) result of extract_from_subgrid(axis 0) for the facet's off0;
+ * accs[f]: (xM_yN_size x yN_size) accumulator NAF_MNAF, ACCUMULATED into. */
+int swiftly_b200_subgrid_to_facets(const swiftly_b200* plan, int n_facets,
+                                   const swiftly_b200_lines* blocks,
+                                   const swiftly_b200_lines* accs, const int64_t* facet_off1,
+                                   int64_t subgrid_off1, void* stream);
+/* Fold a finished subgrid column into n_facets facet accumulators in ONE launch: per facet
+ * `finish_facet(acc, facet_off1, size, axis=1)`, optional mask1, `add_to_facet(., subgrid_off0,
+ * axis=0, out=facet_acc)` (api_helper.py:155-179).  facet_accs[f]: (yN_size x facet_size)
+ * accumulator MNAF_BMNAF, ACCUMULATED into; mask1 or mask1[f] may be NULL. */
+int swiftly_b200_fold_column(const swiftly_b200* plan, int n_facets,
+                             const swiftly_b200_lines* accs,
+                             const swiftly_b200_lines* facet_accs, const int64_t* facet_off1,
+                             const double* const* mask1, int64_t subgrid_off0, void* stream);
+
 /* xM_size / xM_yN_size if the fused kernel exists for this plan, else 0. */
 int swiftly_b200_sum_finish_axis_supported(const swiftly_b200* plan);
 

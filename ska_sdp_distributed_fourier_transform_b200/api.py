@@ -466,17 +466,47 @@ class SwiftlyBackward:
         self.task_queue = _TaskQueue(queue_size)
         self.lru = _LRU(lru_backward)
         self._client = client
+        # fused kernels: one launch per subgrid for all facets (extract axis 1 + accumulate
+        # column), one launch per finished column for all facets (finish axis 1 + mask + add
+        # axis 0); otherwise the reference's task bodies run primitive by primitive
+        self._fused = bool(hasattr(self.core, "subgrid_to_facets")
+                           and getattr(self.core, "fused_backward_supported", lambda: False)())
+        self._masks1 = None
 
     def add_new_subgrid_task(self, subgrid_config, new_subgrid_task):
         """Fold one subgrid into the facet accumulators."""
         off0, off1 = subgrid_config.off0, subgrid_config.off1
         subgrid = _to_device(_resolve(new_subgrid_task), self.device)
-        pieces = prepare_and_split_subgrid(
-            self.core, subgrid, [off0, off1], self.facets_config_list
-        )
-        done = self.update_off0_NAF_MNAFs(off0, off1, pieces)
+        if self._fused:
+            done = self._add_subgrid_fused(subgrid, off0, off1)
+        else:
+            pieces = prepare_and_split_subgrid(
+                self.core, subgrid, [off0, off1], self.facets_config_list
+            )
+            done = self.update_off0_NAF_MNAFs(off0, off1, pieces)
         self.task_queue.process(done)
         return done
+
+    def _add_subgrid_fused(self, subgrid, off0, off1):
+        core = self.core
+        prepared = core.prepare_subgrid(subgrid, (off0, off1))
+        blocks = {}
+        for cfg in self.facets_config_list:
+            if cfg.off0 not in blocks:
+                blocks[cfg.off0] = core.extract_from_subgrid(prepared, cfg.off0, axis=0)
+        column = self.lru.get(off0)
+        if column is None:
+            shape = (core.xM_yN_size, core.yN_size)
+            column = [torch.zeros(shape, dtype=torch.complex128, device=self.device)
+                      for _ in self.facets_config_list]
+        core.subgrid_to_facets(
+            [blocks[cfg.off0] for cfg in self.facets_config_list], column,
+            [cfg.off1 for cfg in self.facets_config_list], off1)
+        tasks = [DeviceTask(column[-1])] if column else []
+        old_off0, old_column = self.lru.set(off0, column)
+        if old_off0 is not None:
+            self.update_MNAF_BMNAFs(old_off0, old_column)
+        return tasks
 
     def update_off0_NAF_MNAFs(self, off0, off1, new_NAF_NAF_tasks):
         """Accumulate along axis 1 into the column accumulators of column ``off0``."""
@@ -495,6 +525,18 @@ class SwiftlyBackward:
 
     def update_MNAF_BMNAFs(self, off0, new_NAF_MNAFs):
         """Finish a subgrid column along axis 1 and fold it into the facets (axis 0)."""
+        if self._fused:
+            core = self.core
+            for j, cfg in enumerate(self.facets_config_list):
+                if self.MNAF_BMNAFs_persist[j] is None:
+                    self.MNAF_BMNAFs_persist[j] = torch.zeros(
+                        (core.yN_size, cfg.size), dtype=torch.complex128, device=self.device)
+            if self._masks1 is None:
+                self._masks1 = [_device_mask(cfg.mask1, self.device)
+                                for cfg in self.facets_config_list]
+            core.fold_column(new_NAF_MNAFs, self.MNAF_BMNAFs_persist,
+                             [cfg.off1 for cfg in self.facets_config_list], self._masks1, off0)
+            return self.MNAF_BMNAFs_persist
         self.MNAF_BMNAFs_persist = [
             accumulate_facet(self.core, col, acc, cfg, off0)
             for cfg, col, acc in zip(

@@ -341,6 +341,12 @@ class SwiftlyCoreB200:
         """True if the fused subgrid kernels exist for this (xM_yN_size, xM_size) pair."""
         return self._lib.swiftly_b200_sum_finish_axis_supported(self._plan) > 0
 
+    def fused_backward_supported(self):
+        """True if the fused backward kernels can run this plan's FFT lengths."""
+        from .swift_configs import fft_length_supported  # pylint: disable=import-outside-toplevel
+
+        return fft_length_supported(self.xM_yN_size) and fft_length_supported(self.yN_size)
+
     def extract_column(self, BF_F, subgrid_off0, facet_off1, out=None):
         """``extract_column`` task of the reference (api_helper.py:200-210) as ONE kernel.
 
@@ -517,3 +523,89 @@ class SwiftlyCoreB200:
         )
         _lib.check(self._lib, rc)
         return out
+
+    # ------------------------------------------------------------------ fused backward path
+    def _lines_array(self, tensors, shape_check):
+        arr = (_lib.Lines * len(tensors))()
+        for k, t in enumerate(tensors):
+            self._check_tensor(t)
+            if t.dtype != torch.complex128 or t.dim() != 2 or t.stride(1) != 1:
+                raise ValueError("need row-contiguous 2-D complex128 device tensors")
+            shape_check(t)
+            arr[k] = self._describe(t, 1)
+        return arr
+
+    def subgrid_to_facets(self, blocks, accs, facet_off1s, subgrid_off1):
+        """One subgrid into the column accumulators of many facets, ONE launch per <= 64 facets.
+
+        Per facet: ``extract_from_subgrid(block, facet_off1, axis=1)`` and
+        ``add_to_facet(., subgrid_off1, axis=1, out=acc)`` (api_helper.py:115-152).
+        ``blocks[f]``: ``(xM_yN_size, xM_size)``; ``accs[f]``: ``(xM_yN_size, yN_size)``, added to.
+        """
+        m, xM, yN = self.xM_yN_size, self.xM_size, self.yN_size
+
+        def chk_b(t):
+            if tuple(t.shape) != (m, xM):
+                raise ValueError(f"block has shape {tuple(t.shape)}, expected {(m, xM)}!")
+
+        def chk_a(t):
+            if tuple(t.shape) != (m, yN):
+                raise ValueError(f"accumulator has shape {tuple(t.shape)}, expected {(m, yN)}!")
+
+        for lo in range(0, len(blocks), 64):
+            hi = min(lo + 64, len(blocks))
+            din = self._lines_array(blocks[lo:hi], chk_b)
+            dout = self._lines_array(accs[lo:hi], chk_a)
+            offs = (ctypes.c_int64 * (hi - lo))(*[int(o) for o in facet_off1s[lo:hi]])
+            rc = self._lib.swiftly_b200_subgrid_to_facets(
+                self._plan, hi - lo, din, dout, offs, int(subgrid_off1), self._stream(accs[lo]))
+            _lib.check(self._lib, rc)
+        return accs
+
+    def fold_column(self, accs, facet_accs, facet_off1s, masks1, subgrid_off0):
+        """Fold a finished subgrid column into many facet accumulators, ONE launch per <= 64.
+
+        Per facet: ``finish_facet(acc, facet_off1, size, axis=1)``, mask, and
+        ``add_to_facet(., subgrid_off0, axis=0, out=facet_acc)`` (api_helper.py:155-179).
+        ``facet_accs[f]``: ``(yN_size, facet_size)``, added to; ``masks1[f]``: float64 device
+        tensor of the facet size or None.
+        """
+        m, yN = self.xM_yN_size, self.yN_size
+
+        def chk_a(t):
+            if tuple(t.shape) != (m, yN):
+                raise ValueError(f"accumulator has shape {tuple(t.shape)}, expected {(m, yN)}!")
+
+        def chk_f(t):
+            if t.shape[0] != yN:
+                raise ValueError(f"facet accumulator has {t.shape[0]} rows, expected {yN}!")
+
+        keep = []
+        for lo in range(0, len(accs), 64):
+            hi = min(lo + 64, len(accs))
+            din = self._lines_array(accs[lo:hi], chk_a)
+            dout = (_lib.Lines * (hi - lo))()
+            for k, t in enumerate(facet_accs[lo:hi]):
+                self._check_tensor(t)
+                if t.dtype != torch.complex128 or t.dim() != 2 or t.stride(1) != 1:
+                    raise ValueError("need row-contiguous 2-D complex128 device tensors")
+                chk_f(t)
+                # lines = rows (yN of them), line length = facet size
+                dout[k] = _lib.Lines(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), 1,
+                                     _lib.DEVICE)
+            offs = (ctypes.c_int64 * (hi - lo))(*[int(o) for o in facet_off1s[lo:hi]])
+            mptrs = (ctypes.c_void_p * (hi - lo))()
+            for k, mk in enumerate(masks1[lo:hi]):
+                if mk is None:
+                    mptrs[k] = None
+                else:
+                    mk = mk.to(torch.float64).contiguous()
+                    if mk.numel() != facet_accs[lo + k].shape[1]:
+                        raise ValueError("mask must have the facet size")
+                    keep.append(mk)
+                    mptrs[k] = mk.data_ptr()
+            rc = self._lib.swiftly_b200_fold_column(
+                self._plan, hi - lo, din, dout, offs, mptrs, int(subgrid_off0),
+                self._stream(accs[lo]))
+            _lib.check(self._lib, rc)
+        return facet_accs

@@ -253,3 +253,97 @@ extern "C" int swiftly_b200_extract_columns(const swiftly_b200* h, int n_facets,
     op.rm_base = (int)pmod(yN / 2 - m / 2 + sc, yN);
     return run_extract_columns(h, op, false, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------- fused backward path
+// One subgrid -> column accumulators of all facets (SubgridToFacetsOp, kernels.cuh).
+extern "C" int swiftly_b200_subgrid_to_facets(const swiftly_b200* h, int n_facets,
+                                              const swiftly_b200_lines* blocks,
+                                              const swiftly_b200_lines* accs,
+                                              const int64_t* facet_off1, int64_t subgrid_off1,
+                                              void* stream) {
+    if (!h || !blocks || !accs || !facet_off1) return einval("subgrid_to_facets: NULL argument");
+    if (n_facets < 1 || n_facets > SW_MAX_COLUMN_FACETS)
+        return einval("subgrid_to_facets: between 1 and " +
+                      std::to_string(SW_MAX_COLUMN_FACETS) + " facets per call");
+    const int64_t yN = h->yN, xM = h->xM, m = h->m;
+    SubgridToFacetsOp op;
+    for (int f = 0; f < n_facets; ++f) {
+        const swiftly_b200_lines& i = blocks[f];
+        const swiftly_b200_lines& o = accs[f];
+        if (i.location != SWIFTLY_B200_DEVICE || o.location != SWIFTLY_B200_DEVICE)
+            return einval("subgrid_to_facets: device arrays only");
+        if (i.n_lines != m || i.size != xM || i.elem_stride != 1)
+            return einval("subgrid_to_facets: blocks must be xM_yN_size contiguous lines of xM_size");
+        if (o.n_lines != m || o.size != yN || o.elem_stride != 1)
+            return einval("subgrid_to_facets: accumulators must be xM_yN_size lines of yN_size");
+        const int64_t sf = floordiv(facet_off1[f] * xM, h->N);
+        BackFacet& F = op.fac[f];
+        F.in = (const cplx*)i.data;
+        F.out = (cplx*)o.data;
+        F.in_ls = i.line_stride;
+        F.out_ls = o.line_stride;
+        F.sf_m = (int)pmod(sf, m);
+        F.base_x = (int)pmod(xM / 2 - m / 2 + sf, xM);
+    }
+    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    const int64_t sc = floordiv(subgrid_off1 * yN, h->N);
+    op.g.in = nullptr;
+    op.g.out = nullptr;
+    op.g.in_ls = op.g.in_es = op.g.out_ls = op.g.out_es = 0;
+    op.g.n_lines = (int64_t)n_facets * m;
+    op.fn = h->d_Fn;
+    op.m = (int)m;
+    op.xM = (int)xM;
+    op.yN = (int)yN;
+    op.lines_per = (int)m;
+    op.s_m = (int)pmod(sc, m);
+    op.base_y = (int)pmod(yN / 2 - m / 2 + sc, yN);
+    op.scale = 1.0 / (double)m;
+    return run_subgrid_to_facets(h, op, false, (cudaStream_t)stream);
+}
+
+// Fold one finished subgrid column into all facet accumulators (FoldColumnOp, kernels.cuh).
+extern "C" int swiftly_b200_fold_column(const swiftly_b200* h, int n_facets,
+                                        const swiftly_b200_lines* accs,
+                                        const swiftly_b200_lines* facet_accs,
+                                        const int64_t* facet_off1, const double* const* mask1,
+                                        int64_t subgrid_off0, void* stream) {
+    if (!h || !accs || !facet_accs || !facet_off1) return einval("fold_column: NULL argument");
+    if (n_facets < 1 || n_facets > SW_MAX_COLUMN_FACETS)
+        return einval("fold_column: between 1 and " + std::to_string(SW_MAX_COLUMN_FACETS) +
+                      " facets per call");
+    const int64_t yN = h->yN, m = h->m;
+    FoldColumnOp op;
+    for (int f = 0; f < n_facets; ++f) {
+        const swiftly_b200_lines& i = accs[f];
+        const swiftly_b200_lines& o = facet_accs[f];
+        if (i.location != SWIFTLY_B200_DEVICE || o.location != SWIFTLY_B200_DEVICE)
+            return einval("fold_column: device arrays only");
+        if (i.n_lines != m || i.size != yN || i.elem_stride != 1)
+            return einval("fold_column: column accumulators must be xM_yN_size lines of yN_size");
+        if (o.n_lines != yN || o.elem_stride != 1 || o.size > yN - 1)
+            return einval("fold_column: facet accumulators must be yN_size lines of facet size");
+        FoldFacet& F = op.fac[f];
+        F.in = (const cplx*)i.data;
+        F.out = (cplx*)o.data;
+        F.mask = mask1 ? mask1[f] : nullptr;
+        F.in_ls = i.line_stride;
+        F.out_ls = o.line_stride;
+        F.fs = (int)o.size;
+        F.start1 = (int)pmod(yN / 2 - o.size / 2 + facet_off1[f], yN);
+        F.fb_off = (int)((yN - 1) / 2 - o.size / 2);
+        F.pad_ = 0;
+    }
+    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    const int64_t sc = floordiv(subgrid_off0 * yN, h->N);
+    op.g.in = nullptr;
+    op.g.out = nullptr;
+    op.g.in_ls = op.g.in_es = op.g.out_ls = op.g.out_es = 0;
+    op.g.n_lines = (int64_t)n_facets * m;
+    op.fb = h->d_Fb;
+    op.n = (int)yN;
+    op.lines_per = (int)m;
+    op.s0_m = (int)pmod(sc, m);
+    op.base0 = (int)pmod(yN / 2 - m / 2 + sc, yN);
+    return run_fold_column(h, op, false, (cudaStream_t)stream);
+}

@@ -164,6 +164,88 @@ struct ExtractColumnsOp {
     }
 };
 
+// ------------------------------------------------------------------ fused backward ops
+// One subgrid -> the column accumulators of ALL facets in one launch
+// (api_helper.py:115-152 per facet: extract_from_subgrid(axis 1) then accumulate_column =
+// add_to_facet(axis 1)).  Global line L = f * lines_per + t: row t of the (m, xM) block that
+// extract_from_subgrid(axis 0) produced for facet f's off0; the m-point inverse transform of
+// the Fn-weighted window is added at the subgrid's position of facet f's (m, yN) accumulator.
+struct BackFacet {
+    const cplx* in;  // (m, xM) block of the facet's row group
+    cplx* out;       // (m, yN) column accumulator NAF_MNAF of the facet
+    int64_t in_ls, out_ls;
+    int sf_m, base_x;  // facet_off1 * xM // N mod m ; (xM/2 - m/2 + sf) mod xM
+};
+struct SubgridToFacetsOp {
+    Lines g;  // only n_lines is used
+    BackFacet fac[SW_MAX_COLUMN_FACETS];
+    const double* fn;
+    int m, xM, yN, lines_per;
+    int s_m, base_y;  // subgrid_off1 * yN // N mod m ; (yN/2 - m/2 + s) mod yN
+    double scale;     // 1 / m
+    SW_HD cplx load(int64_t line, int q) const {
+        const int f = (int)(line / lines_per);
+        const int t = (int)(line - (int64_t)f * lines_per);
+        const BackFacet& F = fac[f];
+        int tc = wrap_add(q, m / 2, m);
+        int u = wrap_sub(tc, F.sf_m, m);
+        int pos = wrap_add(F.base_x, u, xM);
+        return cscale(ld_stream(F.in + (int64_t)t * F.in_ls + pos), ldg_d(fn + u));
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        const int f = (int)(line / lines_per);
+        const int t = (int)(line - (int64_t)f * lines_per);
+        const BackFacet& F = fac[f];
+        int pc = wrap_add(p, m / 2, m);
+        int w = wrap_add(base_y, wrap_sub(pc, s_m, m), yN);
+        cplx* o = F.out + (int64_t)t * F.out_ls + w;
+        cplx a = *o;
+        *o = mk(a.x + scale * v.x, a.y + scale * v.y);
+    }
+};
+
+// Fold a finished subgrid column into ALL facets in one launch (api_helper.py:155-179 per
+// facet: finish_facet(axis 1), mask, add_to_facet(axis 0)).  Line L = f * lines_per + t: row t
+// of facet f's (m, yN) column accumulator; its yN-point forward transform, cut to the facet
+// size and weighted with Fb (and the facet mask), is added to row
+// (base0 + ((t - s0_m) mod m)) mod yN of the facet's (yN, fs) accumulator.
+struct FoldFacet {
+    const cplx* in;      // (m, yN) column accumulator
+    cplx* out;           // (yN, fs) facet accumulator MNAF_BMNAF
+    const double* mask;  // fs doubles or null
+    int64_t in_ls, out_ls;
+    int fs, start1, fb_off;
+    int pad_;
+};
+struct FoldColumnOp {
+    Lines g;  // only n_lines is used
+    FoldFacet fac[SW_MAX_COLUMN_FACETS];
+    const double* fb;
+    int n, lines_per;   // yN, m
+    int s0_m, base0;    // subgrid_off0 * yN // N mod m ; (yN/2 - m/2 + s0) mod yN
+    SW_HD cplx load(int64_t line, int q) const {
+        const int f = (int)(line / lines_per);
+        const int t = (int)(line - (int64_t)f * lines_per);
+        const FoldFacet& F = fac[f];
+        int qc = wrap_add(q, n / 2, n);
+        return ld_stream(F.in + (int64_t)t * F.in_ls + qc);
+    }
+    SW_HD void store(int64_t line, int p, cplx v) const {
+        const int f = (int)(line / lines_per);
+        const int t = (int)(line - (int64_t)f * lines_per);
+        const FoldFacet& F = fac[f];
+        int pc = wrap_add(p, n / 2, n);
+        int k = wrap_sub(pc, F.start1, n);
+        if (k >= F.fs) return;
+        double w = ldg_d(fb + F.fb_off + k);
+        if (F.mask) w *= ldg_d(F.mask + k);
+        int64_t row = wrap_add(base0, wrap_sub(t, s0_m, lines_per), n);
+        cplx* o = F.out + row * F.out_ls + k;
+        cplx a = *o;
+        *o = mk(a.x + w * v.x, a.y + w * v.y);
+    }
+};
+
 // finish_facet (core.py:452-484): out[k] = Fb_c[k] * fft_c(sum)[(yN/2 - fs//2 + k + off) mod yN]
 struct FinishFacetOp {
     Lines g;

@@ -50,6 +50,8 @@ int run_finish_subgrid(const swiftly_b200* h, const FinishSubgridOp& op, bool li
 int run_prepare_subgrid(const swiftly_b200* h, const PrepareSubgridOp& op, bool line_fastest, cudaStream_t s);
 int run_prepare_facet_pass_a(const swiftly_b200* h, const PrepareFacetPassAOp& op, cudaStream_t s);
 int run_prepare_facet_pass_b(const swiftly_b200* h, const PrepareFacetPassBOp& op, cudaStream_t s);
+int run_subgrid_to_facets(const swiftly_b200* h, const SubgridToFacetsOp& op, bool line_fastest, cudaStream_t s);
+int run_fold_column(const swiftly_b200* h, const FoldColumnOp& op, bool line_fastest, cudaStream_t s);
 int run_extract_columns(const swiftly_b200* h, const ExtractColumnsOp& op, bool line_fastest, cudaStream_t s);
 
 // fused subgrid axis kernel (dispatch_subgrid_axis.cu); `k` carries everything but the tables

@@ -27,7 +27,8 @@ def devof(cfg):
 
 
 def dev(cfg, arr):
-    return torch.from_numpy(numpy.ascontiguousarray(arr)).to(devof(cfg))
+    # clone: on the emulated (CPU) device .to() would alias the numpy array
+    return torch.from_numpy(numpy.ascontiguousarray(arr)).clone().to(devof(cfg))
 
 
 def case_fused_ops_vs_oracle(make_config):
@@ -132,3 +133,41 @@ def case_api_round_trip(make_config, lru_forward, lru_backward, shuffle):
     assert worst_sg < 1e-13
     for fc, task in zip(facet_cfgs, bwd.finish()):
         assert check_facet(cfg.image_size, fc, task.result(), sources) < 3e-10
+
+
+def case_fused_backward_ops_vs_oracle(make_config, W=13.5625, N=256, yB=96, yN=128, xA=52, xM=64,
+                                      **kw):
+    """subgrid_to_facets / fold_column against the unfused oracle chain."""
+    cfg = make_config(W, N, yB, yN, xA, xM, **kw)
+    core = cfg.core
+    oracle = OracleCore(W, N, xM, yN)
+    assert core.fused_backward_supported()
+    m = core.xM_yN_size
+    rng = numpy.random.default_rng(21)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    off1s = [0, 24 * Ny, -9 * Ny]
+    blocks = [pc.rand_c(rng, m, xM) for _ in range(2)]
+    use = [0, 1, 0]  # facet -> block (facets 0 and 2 share a row group)
+    acc0 = [pc.rand_c(rng, m, yN) for _ in off1s]
+    accs = [dev(cfg, a) for a in acc0]
+    sg_off1 = 7 * Nx
+    core.subgrid_to_facets([dev(cfg, blocks[u]) for u in use], accs, off1s, sg_off1)
+    for j, (u, o1) in enumerate(zip(use, off1s)):
+        ref = oracle.add_to_facet(oracle.extract_from_subgrid(blocks[u], o1, axis=1), sg_off1,
+                                  axis=1, out=acc0[j].copy())
+        pc.close(accs[j].cpu().numpy(), ref, what=f"subgrid_to_facets facet {j}")
+    # fold: finish axis 1, mask, add axis 0
+    sizes = [yB, yB - 1, yB]
+    f0 = [pc.rand_c(rng, yN, s) for s in sizes]
+    faccs = [dev(cfg, a) for a in f0]
+    masks = [None, (rng.random(yB - 1) > 0.2).astype(float), None]
+    sg_off0 = -5 * Nx
+    core.fold_column(accs, faccs, off1s,
+                     [None if mk is None else dev(cfg, mk) for mk in masks], sg_off0)
+    for j in range(3):
+        col = accs[j].cpu().numpy()
+        part = oracle.finish_facet(col, off1s[j], sizes[j], axis=1)
+        if masks[j] is not None:
+            part = part * masks[j][None, :]
+        ref = oracle.add_to_facet(part, sg_off0, axis=0, out=f0[j].copy())
+        pc.close(faccs[j].cpu().numpy(), ref, what=f"fold_column facet {j}")

@@ -32,3 +32,11 @@ def test_emu_sparse_facets_shuffled_subgrids():
 @pytest.mark.parametrize("lru_forward,lru_backward,shuffle", [(1, 1, False), (2, 2, True)])
 def test_emu_api_round_trip(lru_forward, lru_backward, shuffle):
     api_cases.case_api_round_trip(make_config, lru_forward, lru_backward, shuffle)
+
+
+def test_emu_fused_backward_ops_vs_oracle():
+    api_cases.case_fused_backward_ops_vs_oracle(make_config)
+    # yN through the 2 x yN/2 split kernel, and a non-power-of-two parameter set (split-F)
+    api_cases.case_fused_backward_ops_vs_oracle(make_config, force_split=True)
+    api_cases.case_fused_backward_ops_vs_oracle(make_config, W=11.0, N=1280, yB=440, yN=640,
+                                                xA=280, xM=320)

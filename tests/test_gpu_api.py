@@ -35,6 +35,14 @@ def test_fused_ops_vs_oracle():
     api_cases.case_fused_ops_vs_oracle(make_config)
 
 
+def test_fused_backward_ops_vs_oracle():
+    api_cases.case_fused_backward_ops_vs_oracle(make_config)
+    api_cases.case_fused_backward_ops_vs_oracle(make_config, W=11.0, N=1280, yB=440, yN=640,
+                                                xA=280, xM=320)
+    api_cases.case_fused_backward_ops_vs_oracle(make_config, N=8192, yB=2048, yN=4096, xA=1024,
+                                                xM=2048)
+
+
 def test_forward_backward_vs_reference_golden(golden_2d):
     api_cases.case_forward_backward_vs_reference_golden(make_config, golden_2d)
 
