@@ -550,8 +550,14 @@ class SwiftlyBackward:
         for old_off0, old_column in self.lru.pop_all():
             self.update_MNAF_BMNAFs(old_off0, old_column)
         tasks = []
-        for cfg, acc in zip(self.facets_config_list, self.MNAF_BMNAFs_persist):
+        for j, cfg in enumerate(self.facets_config_list):
+            # release every accumulator as soon as its facet is finished: (yN, size) goes,
+            # (size, size) stays -- at N=65536 on one GPU the 128 GiB of accumulators and the
+            # 64 GiB of finished facets never coexist
+            acc = self.MNAF_BMNAFs_persist[j]
+            self.MNAF_BMNAFs_persist[j] = None
             facet = finish_facet(self.core, acc, cfg)
+            del acc
             tasks.append(DeviceTask(facet))
         self.task_queue.process(tasks)
         self.task_queue.wait_all_done()
