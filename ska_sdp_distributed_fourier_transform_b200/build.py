@@ -77,7 +77,8 @@ def build(force=False, verbose=False):
         for _, log in results:
             sys.stdout.write(log)
     objs = [o for o, _ in results]
-    cmd = [nvcc(), "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + [
+        "-lcudart"]
     subprocess.run(cmd, check=True)
     return OUT
 

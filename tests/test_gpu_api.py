@@ -112,7 +112,6 @@ def test_catalogue_config_round_trip():
     # a non-power-of-two catalogue entry (yN = 3 * 256): unfused GPU path, analytic check
     params = SWIFT_CONFIGS["1536[1]-n768-512"]
     cfg3 = SwiftlyConfig(**params)
-    assert not cfg3.core.fused_forward_supported() or True
     N3 = cfg3.image_size
     facet_cfgs = make_full_facet_cover(cfg3)
     fwd = SwiftlyForward(cfg3, [(fc, make_facet(N3, fc, sources)) for fc in facet_cfgs])
