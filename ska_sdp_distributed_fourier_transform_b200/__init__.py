@@ -18,6 +18,11 @@ from .api import (  # noqa: F401
 )
 from .api_helper import check_facet, check_subgrid, make_facet, make_subgrid  # noqa: F401
 from .core import SwiftlyCoreB200  # noqa: F401
+from .distributed import (  # noqa: F401
+    SwiftlyBackwardSharded,
+    SwiftlyForwardSharded,
+    partition_facets,
+)
 from .fourier_algorithm import make_facet_from_sources, make_subgrid_from_sources  # noqa: F401
 from .swift_configs import SWIFT_CONFIGS  # noqa: F401
 
@@ -28,6 +33,9 @@ __all__ = [
     "SwiftlyForward",
     "SwiftlyBackward",
     "SwiftlyCoreB200",
+    "SwiftlyForwardSharded",
+    "SwiftlyBackwardSharded",
+    "partition_facets",
     "SWIFT_CONFIGS",
     "check_facet",
     "check_subgrid",

@@ -324,3 +324,73 @@ class SwiftlyForwardSharded:
                 else:
                     results[idx] = DeviceTask(out)
         return results
+
+
+class SwiftlyBackwardSharded:
+    """Subgrid -> facet accumulation with the facets sharded over a process group.
+
+    Mirror image of :class:`SwiftlyForwardSharded`: every facet
+    accumulator lives on the rank that owns the facet (:func:`partition_facets`), so the only
+    exchange is getting each subgrid to every rank -- subgrids are processed in batches of
+    ``world_size``, subgrid ``b`` of a batch is supplied by rank ``b`` (the rank that owns it
+    after the forward transform) and one ``all_gather`` per batch replicates the batch; there
+    is no reduction.  Each rank then folds the batch into its own facets with the fused
+    backward kernels of :class:`~.api.SwiftlyBackward`.
+
+    Calls are collective: every rank calls :meth:`add_subgrid_tasks` with the same subgrid
+    configs; ``tasks[i]`` must be given on rank ``i % world_size`` (others pass ``None``).
+    """
+
+    def __init__(self, swiftly_config, facets_config_list, lru_backward=1, queue_size=20,
+                 group=None):
+        from .api import SwiftlyBackward  # pylint: disable=import-outside-toplevel
+
+        self.config = swiftly_config
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.facets_config_list = list(facets_config_list)
+        self.owner = partition_facets(self.facets_config_list, self.world)
+        self.local_idx = [i for i, o in enumerate(self.owner) if o == self.rank]
+        self.device = _device_of(swiftly_config.core)
+        self._local = SwiftlyBackward(
+            swiftly_config, [self.facets_config_list[i] for i in self.local_idx],
+            lru_backward=lru_backward, queue_size=queue_size)
+
+    def add_subgrid_tasks(self, subgrid_configs, tasks):
+        """Fold ``subgrid_configs`` into the local facets (collective call)."""
+        subgrid_configs = list(subgrid_configs)
+        tasks = list(tasks)
+        if len(tasks) != len(subgrid_configs):
+            raise ValueError("one task entry (or None) per subgrid config")
+        sizes = {sg.size for sg in subgrid_configs}
+        if len(sizes) > 1:
+            raise ValueError("all subgrids of one call must have the same size")
+        for lo in range(0, len(subgrid_configs), self.world):
+            batch = subgrid_configs[lo:lo + self.world]
+            mine = lo + self.rank
+            xA = batch[0].size
+            if self.rank < len(batch):
+                data = tasks[mine]
+                if data is None:
+                    raise ValueError(f"rank {self.rank} must supply subgrid {mine}")
+                from .api import _resolve, _to_device  # pylint: disable=import-outside-toplevel
+
+                local = _to_device(_resolve(data), self.device).contiguous()
+            else:
+                local = torch.zeros((xA, xA), dtype=torch.complex128, device=self.device)
+            if self.world > 1:
+                gathered = torch.empty((self.world, xA, xA), dtype=torch.complex128,
+                                       device=self.device)
+                dist.all_gather_into_tensor(
+                    torch.view_as_real(gathered).reshape(self.world, -1),
+                    torch.view_as_real(local).reshape(1, -1), group=self.group)
+            else:
+                gathered = local[None]
+            for b, sg in enumerate(batch):
+                self._local.add_new_subgrid_task(sg, gathered[b])
+
+    def finish(self):
+        """Finish the local facets; returns ``{facet index: DeviceTask}`` for this rank."""
+        tasks = self._local.finish()
+        return dict(zip(self.local_idx, tasks))

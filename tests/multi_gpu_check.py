@@ -64,6 +64,25 @@ def main():
         worst = 0.0
         for r, i in zip(ref, mine):
             worst = max(worst, float(numpy.abs(tasks[i].result() - r).max() / numpy.abs(r).max()))
+        # sharded backward on the same data: every rank supplies its own subgrids
+        from oracle.swiftly_oracle import backward_reference_order
+        from ska_sdp_distributed_fourier_transform_b200.distributed import SwiftlyBackwardSharded
+
+        bwd = SwiftlyBackwardSharded(cfg, facet_cfgs, lru_backward=1)
+        bwd.add_subgrid_tasks(sgs, [tasks.get(i) for i in range(len(sgs))])
+        back = bwd.finish()
+        if back:
+            full_ref = forward_reference_order(
+                oracle, facets, [(c.off0, c.off1) for c in facet_cfgs],
+                [(s.off0, s.off1) for s in sgs], xA,
+                subgrid_masks=[(s.mask0, s.mask1) for s in sgs])
+            back_ref = backward_reference_order(
+                oracle, full_ref, [(s.off0, s.off1) for s in sgs],
+                [(c.off0, c.off1) for c in facet_cfgs], yB,
+                facet_masks=[(c.mask0, c.mask1) for c in facet_cfgs])
+            bscale = max(float(numpy.abs(b).max()) for b in back_ref)
+            for i, task in back.items():
+                worst = max(worst, float(numpy.abs(task.result() - back_ref[i]).max() / bscale))
         t = torch.tensor([worst], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
