@@ -28,34 +28,34 @@ def close(a, ref, rtol=TIGHT, what=""):
     assert err <= rtol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
 
 
-def check_1d_chain(core, oracle, yB, xA, facet_off, sg_off, rng):
+def check_1d_chain(core, oracle, yB, xA, facet_off, sg_off, rng, rtol=TIGHT):
     facet = rand_c(rng, yB)
     prep = core.prepare_facet(facet, facet_off, axis=0)
     oprep = oracle.prepare_facet(facet, facet_off, axis=0)
-    close(prep, oprep, what="prepare_facet")
+    close(prep, oprep, rtol=rtol, what="prepare_facet")
     contrib = core.extract_from_facet(oprep, sg_off, axis=0)
     ocontrib = oracle.extract_from_facet(oprep, sg_off, axis=0)
     assert numpy.array_equal(contrib, ocontrib), "extract_from_facet must be exact"
     acc = core.add_to_subgrid(ocontrib, facet_off, axis=0)
     oacc = oracle.add_to_subgrid(ocontrib, facet_off, axis=0)
-    close(acc, oacc, what="add_to_subgrid")
+    close(acc, oacc, rtol=rtol, what="add_to_subgrid")
     sg = core.finish_subgrid(oacc, sg_off, xA)
-    close(sg, oracle.finish_subgrid(oacc, sg_off, xA), what="finish_subgrid")
+    close(sg, oracle.finish_subgrid(oacc, sg_off, xA), rtol=rtol, what="finish_subgrid")
     subgrid = rand_c(rng, xA)
     psg = core.prepare_subgrid(subgrid, sg_off)
     opsg = oracle.prepare_subgrid(subgrid, sg_off)
-    close(psg, opsg, what="prepare_subgrid")
+    close(psg, opsg, rtol=rtol, what="prepare_subgrid")
     ext = core.extract_from_subgrid(opsg, facet_off, axis=0)
     oext = oracle.extract_from_subgrid(opsg, facet_off, axis=0)
-    close(ext, oext, what="extract_from_subgrid")
+    close(ext, oext, rtol=rtol, what="extract_from_subgrid")
     accf = core.add_to_facet(oext, sg_off, axis=0)
     oaccf = oracle.add_to_facet(oext, sg_off, axis=0)
     assert numpy.array_equal(accf, oaccf), "add_to_facet must be exact"
     fin = core.finish_facet(oaccf, facet_off, yB, axis=0)
-    close(fin, oracle.finish_facet(oaccf, facet_off, yB, axis=0), what="finish_facet")
+    close(fin, oracle.finish_facet(oaccf, facet_off, yB, axis=0), rtol=rtol, what="finish_facet")
 
 
-def check_2d_axis(core, oracle, yB, axis, other, facet_off, sg_off, rng):
+def check_2d_axis(core, oracle, yB, axis, other, facet_off, sg_off, rng, rtol=TIGHT):
     """Every primitive along ``axis`` of a 2-D array with ``other`` lines."""
     yN, xM, m = oracle.yN_size, oracle.xM_size, oracle.xM_yN_size
 
@@ -66,24 +66,24 @@ def check_2d_axis(core, oracle, yB, axis, other, facet_off, sg_off, rng):
 
     facet = rand_c(rng, *shp(yB))
     oprep = oracle.prepare_facet(facet, facet_off, axis=axis)
-    close(core.prepare_facet(facet, facet_off, axis=axis), oprep, what=f"prepare_facet ax{axis}")
+    close(core.prepare_facet(facet, facet_off, axis=axis), oprep, rtol=rtol, what=f"prepare_facet ax{axis}")
     ocontrib = oracle.extract_from_facet(oprep, sg_off, axis=axis)
     assert numpy.array_equal(core.extract_from_facet(oprep, sg_off, axis=axis), ocontrib)
     acc0 = rand_c(rng, *shp(xM))
     oacc = oracle.add_to_subgrid(ocontrib, facet_off, axis=axis, out=acc0.copy())
     acc = core.add_to_subgrid(ocontrib, facet_off, axis=axis, out=acc0.copy())
-    close(acc, oacc, what=f"add_to_subgrid ax{axis} (accumulate)")
+    close(acc, oacc, rtol=rtol, what=f"add_to_subgrid ax{axis} (accumulate)")
     close(core.add_to_subgrid(ocontrib, facet_off, axis=axis),
-          oracle.add_to_subgrid(ocontrib, facet_off, axis=axis), what="add_to_subgrid (fresh)")
+          oracle.add_to_subgrid(ocontrib, facet_off, axis=axis), rtol=rtol, what="add_to_subgrid (fresh)")
     close(core.finish_facet(oprep, facet_off, yB, axis=axis),
-          oracle.finish_facet(oprep, facet_off, yB, axis=axis), what=f"finish_facet ax{axis}")
+          oracle.finish_facet(oprep, facet_off, yB, axis=axis), rtol=rtol, what=f"finish_facet ax{axis}")
     oext = oracle.extract_from_subgrid(oacc, facet_off, axis=axis)
     close(core.extract_from_subgrid(oacc, facet_off, axis=axis), oext,
           what=f"extract_from_subgrid ax{axis}")
     accf0 = rand_c(rng, *shp(yN))
     oaccf = oracle.add_to_facet(oext, sg_off, axis=axis, out=accf0.copy())
     accf = core.add_to_facet(oext, sg_off, axis=axis, out=accf0.copy())
-    close(accf, oaccf, what=f"add_to_facet ax{axis}")
+    close(accf, oaccf, rtol=rtol, what=f"add_to_facet ax{axis}")
     assert m == ocontrib.shape[axis]
 
 

@@ -1,0 +1,58 @@
+"""
+Randomised parity (hypothesis) of the eight primitives on the host-emulated kernels:
+parameter sets with power-of-two and F * 2^k lengths, odd / even facet and subgrid sizes,
+offsets anywhere in [-3N, 3N] (multiples of the offset steps), 1-D and 2-D along both axes.
+"""
+
+import numpy
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle.swiftly_oracle import OracleCore
+from tests import parity_cases as pc
+from tests.emu_support import emu_core_class
+
+# (N, xM, yN): m = xM * yN / N must be an integer >= 16 with supported lengths
+PARAM_SETS = [
+    (256, 64, 128), (512, 128, 128), (512, 64, 256), (1024, 256, 512), (2048, 256, 1024),
+    (768, 192, 384), (1280, 320, 640), (1536, 512, 768), (1792, 256, 1792), (2304, 576, 1152),
+]
+_cores = {}
+
+
+def cores(idx):
+    if idx not in _cores:
+        N, xM, yN = PARAM_SETS[idx]
+        _cores[idx] = (emu_core_class()(11.0, N, xM, yN), OracleCore(11.0, N, xM, yN))
+    return _cores[idx]
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck))
+@given(idx=st.integers(0, len(PARAM_SETS) - 1), fo=st.integers(-3, 3), so=st.integers(-3, 3),
+       fk=st.integers(0, 40), sk=st.integers(0, 40), yb_frac=st.floats(0.2, 0.85),
+       xa_frac=st.floats(0.2, 1.0), seed=st.integers(0, 2**31 - 1), axis=st.integers(0, 1),
+       other=st.integers(1, 9))
+def test_fuzz_primitives(idx, fo, so, fk, sk, yb_frac, xa_frac, seed, axis, other):
+    core, oracle = cores(idx)
+    N, xM, yN = PARAM_SETS[idx]
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    facet_off = fo * N + fk * Ny
+    sg_off = so * N + sk * Nx
+    yB = max(1, min(yN - 1, int(yb_frac * yN)))
+    xA = max(1, min(xM, int(xa_frac * xM)))
+    rng = numpy.random.default_rng(seed)
+    # Fb grows steeply towards yB -> yN (1 / PSWF): the rounding of the yN-point transform is
+    # amplified by max(Fb) in finish_facet, hence 1e-10 here instead of the 1e-12 of the fixed cases
+    pc.check_1d_chain(core, oracle, yB, xA, facet_off, sg_off, rng, rtol=1e-10)
+    pc.check_2d_axis(core, oracle, yB, axis, other, facet_off, sg_off, rng, rtol=1e-10)
+
+
+@pytest.mark.parametrize("idx", [0, 5])
+def test_fuzz_degenerate_sizes(idx):
+    """size-1 facets / subgrids and the largest legal facet (yN - 1)."""
+    core, oracle = cores(idx)
+    N, xM, yN = PARAM_SETS[idx]
+    rng = numpy.random.default_rng(3)
+    pc.check_1d_chain(core, oracle, 1, 1, 0, 0, rng)
+    pc.check_1d_chain(core, oracle, yN - 1, xM, core.facet_off_step, -core.subgrid_off_step, rng,
+                      rtol=1e-7)
