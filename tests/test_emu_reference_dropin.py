@@ -78,3 +78,46 @@ def test_reference_unit_test_functions_accept_our_core(ref):
     mod.test_base_params_check_params("numpy")
     mod.test_facet_to_subgrid_dft_2d("numpy")
     mod.test_subgrid_to_facet_dft_2d("numpy")
+
+
+def test_unmodified_reference_native_backend_runs_on_our_library(ref):
+    """The reference's `SwiftlyCoreFunc` (backend="ska_sdp_func") binds
+    `ska_sdp_func.fourier_transforms.swiftly.Swiftly`; with our ska_sdp_func-shaped adapter in
+    that seat (emulated kernels here) the reference's own unit tests pass UNMODIFIED, strided
+    transposed views (axis 0) included."""
+    import importlib.util
+
+    from ska_sdp_distributed_fourier_transform_b200 import _lib, sdp_func_compat
+    from tests.emu_support import emu_core_class
+
+    emu_core_class()  # builds / loads the emulated library
+    emu_cls = emu_core_class()
+    lib = emu_cls(13.5625, 256, 64, 128)._lib
+
+    class EmuSwiftly(sdp_func_compat.Swiftly):
+        def __init__(self, N, yN_size, xM_size, W):
+            real = _lib.load
+            _lib.load = lambda path=None: lib
+            try:
+                super().__init__(N, yN_size, xM_size, W)
+            finally:
+                _lib.load = real
+
+    native = sys.modules["ska_sdp_func.fourier_transforms.swiftly"]
+    old = native.Swiftly
+    native.Swiftly = EmuSwiftly
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "ref_test_core_native", "/root/reference/tests/test_core.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        backend = "ska_sdp_func"
+        mod.test_base_params_fundamental(backend)
+        mod.test_base_params_derived(backend)
+        mod.test_base_params_check_params(backend)
+        mod.test_facet_to_subgrid_dft_2d(backend)
+        mod.test_subgrid_to_facet_dft_2d(backend)
+        mod.test_facet_to_subgrid_basic(227, 415, backend)
+        mod.test_subgrid_to_facet_basic(228, 416, backend)
+    finally:
+        native.Swiftly = old
