@@ -56,3 +56,48 @@ def test_fuzz_degenerate_sizes(idx):
     pc.check_1d_chain(core, oracle, 1, 1, 0, 0, rng)
     pc.check_1d_chain(core, oracle, yN - 1, xM, core.facet_off_step, -core.subgrid_off_step, rng,
                       rtol=1e-7)
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
+@given(n_src=st.integers(1, 9), seed=st.integers(0, 2**31 - 1), axis=st.integers(0, 1),
+       sk=st.integers(-40, 40), use_mask=st.booleans(), contrib_sized=st.booleans())
+def test_fuzz_fused_sum_finish(n_src, seed, axis, sk, use_mask, contrib_sized):
+    """Fused sum-and-finish kernel with arbitrary source sets: random facet offsets (any
+    overlap pattern -> round scheduling, tiling shortcut on/off), both axes, masks."""
+    import torch
+
+    core, oracle = cores(0)  # N=256, xM=64, yN=128, m=32
+    N, xM, yN = PARAM_SETS[0]
+    m = core.xM_yN_size
+    rng = numpy.random.default_rng(seed)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    sg_off = sk * Nx
+    offs = [int(rng.integers(-64, 64)) * Ny for _ in range(n_src)]
+    size = m if contrib_sized else yN
+    lines, sz = 7, int(rng.integers(1, xM + 1))
+    shape = (lines, size) if axis == 1 else (size, lines)
+    srcs = [pc.rand_c(rng, *shape) for _ in range(n_src)]
+    mask = (rng.random(sz) > 0.3).astype(float) if use_mask else None
+    out = torch.empty((lines, sz) if axis == 1 else (sz, lines), dtype=torch.complex128)
+    core.sum_finish_axis([(torch.from_numpy(s.copy()), o) for s, o in zip(srcs, offs)], out,
+                         axis=axis, subgrid_off=sg_off,
+                         mask=None if mask is None else torch.from_numpy(mask))
+    acc = None
+    for s, o in zip(srcs, offs):
+        c = s if contrib_sized else oracle.extract_from_facet(s, sg_off, axis=axis)
+        acc = oracle.add_to_subgrid(c, o, axis=axis, out=acc)
+    fin = [oracle.finish_subgrid(line, sg_off, sz) for line in (acc if axis == 1 else acc.T)]
+    ref = numpy.array(fin)
+    if mask is not None:
+        ref = ref * mask[None, :]
+    if axis == 0:
+        ref = ref.T
+    pc.close(out.numpy(), ref, rtol=1e-11, what="fused sum_finish_axis")
+
+
+def test_core_pickles_by_parameters():
+    """Like SwiftlyCoreFunc (core.py:513-525) the core pickles by constructor arguments."""
+    core, _ = cores(0)
+    state = core.__getstate__()
+    assert state == {"W": 11.0, "N": 256, "xM_size": 64, "yN_size": 128, "device": 0}
+    assert repr(core).endswith("(W=11.0, N=256, xM_size=64, yN_size=128)")
