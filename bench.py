@@ -372,6 +372,11 @@ def _main_gpu(args):
     contributions = runner.contributions_per_step
     value = contributions / (ms * 1e-3)
 
+    parity = None
+    if not args.no_selfcheck:
+        parity = runner.selfcheck()  # raises above 1e-9; collective at N > 1
+        note(f"self-check: max rel err {parity['parity_max_rel_err']:.2e} "
+             f"({parity['subgrids_checked']} subgrids)")
     extra = {}
     if rank == 0 or world > 1:
         extra = runner.kernel_rooflines(hbm_gbs, step_ms=ms) if not args.no_roofline else {}
@@ -399,6 +404,9 @@ def _main_gpu(args):
         "step_ms": times, "gpu_launches": runner.launches_per_step,
         "clocks": clocks,
     }
+    if parity is not None:
+        line["parity_max_rel_err"] = parity["parity_max_rel_err"]
+        line["parity_check"] = parity
     if world > 1:
         line["config"]["exchange"] = runner.exchange_used
     if extra:
@@ -425,6 +433,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true",
+                    help="skip the output parity check that follows the timed steps")
+    ap.add_argument("--selfcheck", action="store_true", help="(default) kept for symmetry")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],

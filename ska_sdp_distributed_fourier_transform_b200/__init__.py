@@ -16,13 +16,14 @@ from .api import (  # noqa: F401
     make_full_facet_cover,
     make_full_subgrid_cover,
 )
-from .api_helper import check_facet, check_subgrid, make_facet, make_subgrid  # noqa: F401
-from .core import SwiftlyCoreB200  # noqa: F401
-from .distributed import (  # noqa: F401
-    SwiftlyBackwardSharded,
-    SwiftlyForwardSharded,
-    partition_facets,
+from .api_helper import (  # noqa: F401
+    check_facet,
+    check_subgrid,
+    make_facet,
+    make_facet_device,
+    make_subgrid,
 )
+from .core import SwiftlyCoreB200  # noqa: F401
 from .fourier_algorithm import make_facet_from_sources, make_subgrid_from_sources  # noqa: F401
 from .swift_configs import SWIFT_CONFIGS  # noqa: F401
 
@@ -41,10 +42,24 @@ __all__ = [
     "check_subgrid",
     "make_subgrid",
     "make_facet",
+    "make_facet_device",
     "make_full_facet_cover",
     "make_full_subgrid_cover",
     "make_facet_from_sources",
     "make_subgrid_from_sources",
 ]
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+_SHARDED = ("SwiftlyBackwardSharded", "SwiftlyForwardSharded", "partition_facets")
+
+
+def __getattr__(name):
+    # the sharded drivers need torch.distributed; everything else (numpy-mode core,
+    # sdp_func_compat) must import without it
+    if name in _SHARDED:
+        from . import distributed  # pylint: disable=import-outside-toplevel
+
+        return getattr(distributed, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+

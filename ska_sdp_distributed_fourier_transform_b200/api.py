@@ -100,8 +100,10 @@ class SwiftlyConfig:
     :param xA_size: subgrid size
     :param xM_size: padded subgrid size
     :param dask_client: accepted for compatibility, ignored
-    :param backend: ``"b200"`` (alias ``"cuda"``); the reference's CPU backends
-        (``"numpy"``, ``"ska_sdp_func"``) are not part of this package
+    :param backend: ``"b200"`` (alias ``"cuda"``); the reference's backend names
+        (``"numpy"``, ``"ska_sdp_func"``) are accepted and run on the same CUDA core
+        (with a log warning) so that a reference driver only changes its import; any
+        other name raises ``ValueError`` like the reference (api.py:137-143)
     :param device: CUDA device index (default: current device)
     :param core: optionally a ready-made object with the eight-primitive interface
     """
@@ -119,7 +121,13 @@ class SwiftlyConfig:
         self.dask_client = dask_client
         if core is not None:
             self._core = core
-        elif backend in ("b200", "cuda"):
+        elif backend in ("b200", "cuda", "numpy", "ska_sdp_func"):
+            if backend in ("numpy", "ska_sdp_func"):
+                # a driver written for the reference passes its CPU backend names
+                # (api.py:137-143); there is no CPU implementation here -- the same
+                # primitives run on the GPU core
+                log.warning("backend=%r requested: this package has no CPU backend, "
+                            "using the B200 CUDA core", backend)
             self._core = SwiftlyCoreB200(W, N, xM_size, yN_size, device=device)
         else:
             raise ValueError(f"Unknown SwiFTly backend: {backend}")
@@ -419,7 +427,11 @@ class SwiftlyForward:
         m = core.xM_yN_size
         shape = (len(self._rows), m, sg.size)
         if self._strips is None or tuple(self._strips.shape) != shape:
-            self._strips = torch.empty(shape, dtype=torch.complex128, device=self.device)
+            # stored TRANSPOSED -- (row, xA, m), contribution index contiguous -- so that the
+            # axis-0 kernel reads unit-stride lines; the axis-1 kernel's finished lines are
+            # scattered into this layout by the TMA engine (bulk tensor stores)
+            self._strips = torch.empty((shape[0], shape[2], shape[1]), dtype=torch.complex128,
+                                       device=self.device).transpose(1, 2)
         mask0 = _device_mask(sg.mask0, self.device)
         mask1 = _device_mask(sg.mask1, self.device)
         core.sum_finish_axis_grouped(

@@ -45,6 +45,43 @@ def make_facet(image_size, facet_config, sources):
     )
 
 
+def make_facet_device(image_size, facet_config, sources, device, out=None):
+    """:func:`make_facet` painted directly on the GPU (no host array, no H2D copy).
+
+    Same pixel rule as ``make_facet_from_sources`` (fourier_algorithm.py:218-264): a source at
+    image coordinate ``x`` lands on pixel ``(x - (off - size // 2)) mod N`` if that is inside
+    the facet; masks multiply.  ``out``: optional ``(size, size)`` complex128 device tensor.
+    """
+    import torch  # pylint: disable=import-outside-toplevel
+
+    size = facet_config.size
+    if out is None:
+        out = torch.zeros((size, size), dtype=torch.complex128, device=device)
+    else:
+        out.zero_()
+    masks = [facet_config.mask0, facet_config.mask1]
+    corner = (facet_config.off0 - size // 2, facet_config.off1 - size // 2)
+    rows, cols, vals = [], [], []
+    for intensity, x0, x1 in sources:
+        p0 = (int(x0) - corner[0]) % image_size
+        p1 = (int(x1) - corner[1]) % image_size
+        if p0 >= size or p1 >= size:
+            continue
+        w = 1.0
+        if masks[0] is not None:
+            w *= float(masks[0][p0])
+        if masks[1] is not None:
+            w *= float(masks[1][p1])
+        rows.append(p0)
+        cols.append(p1)
+        vals.append(complex(intensity) * w)
+    if rows:
+        idx = (torch.tensor(rows, device=out.device), torch.tensor(cols, device=out.device))
+        out.index_put_(idx, torch.tensor(vals, dtype=torch.complex128, device=out.device),
+                       accumulate=True)
+    return out
+
+
 def _rms(diff):
     return numpy.sqrt(numpy.average(numpy.abs(diff) ** 2))
 

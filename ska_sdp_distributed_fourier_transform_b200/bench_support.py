@@ -18,7 +18,9 @@ from .api import (
     make_full_facet_cover,
     make_full_subgrid_cover,
 )
+from .api_helper import make_facet_device
 from .distributed import SwiftlyForwardSharded, partition_facets
+from .fourier_algorithm import make_subgrid_from_sources
 
 MIB = float(1 << 20)
 
@@ -119,6 +121,54 @@ class ForwardBenchRunner:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms if timed else None
+
+    # ------------------------------------------------------------------ output self-check
+    def selfcheck(self, n_sources=8, tol=1e-9):
+        """Parity of the very path the timed steps ran, at this GPU count.
+
+        The facets are repainted ON THE DEVICE with point sources (zero elsewhere), one more
+        complete forward transform runs through the same driver as :meth:`step`, and three
+        subgrids owned by this rank (first / middle / last) are compared with the analytic
+        DFT of the sources (``make_subgrid_from_sources``, fourier_algorithm.py:267-315).
+        Returns the max over ranks of ``max|got - truth| / max|truth|``; raises above ``tol``.
+        """
+        N = self.params["N"]
+        rng = numpy.random.default_rng(20260922)  # same sources on every rank
+        sources = [(float(rng.random()) + 0.5, int(rng.integers(-N // 2, N // 2)),
+                    int(rng.integers(-N // 2, N // 2))) for _ in range(n_sources)]
+        for idx in self.local_idx:
+            make_facet_device(N, self.facet_cfgs[idx], sources, self.device,
+                              out=self.facet_views[idx])
+        owned = [i for i in range(len(self.sg_cfgs)) if i % self.world == self.rank]
+        wanted = sorted({owned[0], owned[len(owned) // 2], owned[-1]}) if owned else []
+        kept = {}
+
+        def consumer(i, sg, tensor):
+            if i in wanted:
+                kept[i] = tensor.clone()
+
+        self._run_forward(self.facet_views, consumer=consumer)
+        torch.cuda.synchronize(self.device)
+        worst = 0.0
+        for i in wanted:
+            sg = self.sg_cfgs[i]
+            truth = make_subgrid_from_sources(sources, N, sg.size, [sg.off0, sg.off1],
+                                              [sg.mask0, sg.mask1])
+            got = kept[i].cpu().numpy()
+            worst = max(worst, float(numpy.abs(got - truth).max() / numpy.abs(truth).max()))
+        checked = len(wanted)
+        if self.world > 1:
+            t = torch.tensor([worst, float(checked)], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t[0:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
+            worst, checked = float(t[0].item()), int(t[1].item())
+        if not worst <= tol:
+            raise RuntimeError(f"bench self-check failed: max relative error {worst:.3e} "
+                               f"over {checked} subgrids exceeds {tol:g}")
+        return {"parity_max_rel_err": worst, "subgrids_checked": checked,
+                "against": f"analytic DFT of {n_sources} point sources painted into the facets "
+                           "on the device; first / middle / last subgrid owned by every rank; "
+                           "max|got - truth| / max|truth|", "tolerance": tol}
 
     # ------------------------------------------------------------------ per-kernel rooflines
     def _time(self, fn, reps=5):

@@ -125,7 +125,8 @@ extern "C" int swiftly_b200_create(double W, int64_t N, int64_t xM, int64_t yN, 
                       ", subgrid size " + std::to_string(xM) + " and facet size " +
                       std::to_string(yN) + "!");
     if (!Fb || !Fn) return einval("Fb / Fn tables must be given");
-    SW_CUDA(cudaSetDevice(device), "cudaSetDevice");
+    DeviceGuard guard(device);
+    if (!guard.ok()) return cuda_fail(guard.err, "cudaSetDevice");
     swiftly_b200* h = new swiftly_b200();
     h->W = W;
     h->N = N;
@@ -136,6 +137,7 @@ extern "C" int swiftly_b200_create(double W, int64_t N, int64_t xM, int64_t yN, 
     h->d_Fb = nullptr;
     h->d_Fn = nullptr;
     h->force_split = 0;
+    h->sg_variant = 0;
     cudaError_t e = cudaMalloc((void**)&h->d_Fb, sizeof(double) * (size_t)(yN > 1 ? yN - 1 : 1));
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_Fn, sizeof(double) * (size_t)h->m);
     if (e == cudaSuccess)
@@ -152,7 +154,7 @@ extern "C" int swiftly_b200_create(double W, int64_t N, int64_t xM, int64_t yN, 
 
 extern "C" void swiftly_b200_destroy(swiftly_b200* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     if (h->d_Fb) cudaFree(h->d_Fb);
     if (h->d_Fn) cudaFree(h->d_Fn);
     for (auto& kv : h->tw) cudaFree(kv.second);
@@ -166,6 +168,11 @@ extern "C" int64_t swiftly_b200_contribution_size(const swiftly_b200* h) { retur
 // test hook (not in the public header): force the 2 x n/2 split path
 extern "C" void swiftly_b200_debug_force_split(swiftly_b200* h, int on) {
     if (h) h->force_split = on;
+}
+
+// test hook (not in the public header): select the fused subgrid kernel variant
+extern "C" void swiftly_b200_debug_sg_variant(swiftly_b200* h, int variant) {
+    if (h) h->sg_variant = variant;
 }
 
 // ------------------------------------------------------------------ host staging
@@ -307,7 +314,7 @@ bool lines_adjacent(const Lines& g) {
     SW_TRY(check_lines(in, out, in_size, out_size, what));                      \
     if (in->n_lines == 0) return SWIFTLY_B200_OK;                               \
     cudaStream_t s = (cudaStream_t)stream;                                      \
-    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");                         \
+    SW_DEVICE_GUARD(h);                         \
     Staged sin, sout;                                                           \
     SW_TRY(stage_in(sin, in, true, s, what " input"));                          \
     SW_TRY(stage_in(sout, out, copy_out, s, what " output"));                   \

@@ -20,7 +20,7 @@ extern "C" int swiftly_b200_extract_column(const swiftly_b200* h, const swiftly_
     if (out->n_lines != m || out->size != yN)
         return einval("extract_column: output must be xM_yN_size lines of yN_size samples");
     if (fs > yN - 1) return einval("extract_column: facet size must be at most yN_size - 1");
-    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    SW_DEVICE_GUARD(h);
     const int64_t sc = floordiv(subgrid_off0 * yN, h->N);
     PrepareFacetOp op;
     op.g.in = (const cplx*)bf_f->data;
@@ -55,8 +55,6 @@ static int sum_finish_groups(const swiftly_b200* h, const swiftly_b200_source* s
                              const int64_t* subgrid_offs, const double* const* masks,
                              void* stream) {
     if (!h || !sources || !out || !group_sizes) return einval("sum_finish_axis: NULL argument");
-    if (n_groups > SW_MAX_GROUPS)
-        return einval("sum_finish_axis: at most " + std::to_string(SW_MAX_GROUPS) + " groups");
     if (out->location != SWIFTLY_B200_DEVICE) return einval("sum_finish_axis: device arrays only");
     const int64_t yN = h->yN, xM = h->xM, m = h->m;
     const int conc = subgrid_axis_conc((int)m, (int)xM);
@@ -68,13 +66,12 @@ static int sum_finish_groups(const swiftly_b200* h, const swiftly_b200_source* s
     if (n_groups < 1) return einval("sum_finish_axis: need at least one group");
     const int64_t sz = out->size;
     if (sz > xM) return einval("sum_finish_axis: subgrid size exceeds padded subgrid size");
-    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    SW_DEVICE_GUARD(h);
 
     // per group: schedule sources into rounds of `conc` with pairwise disjoint windows
     std::vector<std::vector<std::vector<int>>> rounds((size_t)n_groups);
     std::vector<int> pos_of;
     int first = 0;
-    size_t max_rounds = 1;
     for (int g = 0; g < n_groups; ++g) {
         if (group_sizes[g] < 0) return einval("sum_finish_axis: negative group size");
         for (int i = first; i < first + group_sizes[g]; ++i) {
@@ -105,63 +102,99 @@ static int sum_finish_groups(const swiftly_b200* h, const swiftly_b200_source* s
             if (!placed) rounds[g].push_back(std::vector<int>(1, i));
         }
         first += group_sizes[g];
-        if (rounds[g].size() > max_rounds) max_rounds = rounds[g].size();
     }
-    const int slots = (int)max_rounds * conc;
-    if ((int64_t)slots * n_groups > SW_MAX_SOURCES)
-        return einval("sum_finish_axis: too many sources for one launch (" +
-                      std::to_string(first) + " in " + std::to_string(n_groups) + " groups)");
-    SubgridAxisArgs a;
-    for (int i = 0; i < SW_MAX_SOURCES; ++i) {
-        a.src[i].base = nullptr;
-        a.src[i].ls = a.src[i].es = 0;
-        a.src[i].wbase = a.src[i].s_m = a.src[i].sf_m = a.src[i].pos_base = 0;
-        a.src[i].wmod = 1;
-    }
-    for (int g = 0; g < n_groups; ++g) {
-        const int64_t sc = floordiv(subgrid_offs[g] * yN, h->N);
-        for (size_t r = 0; r < rounds[g].size(); ++r) {
-            for (size_t c = 0; c < rounds[g][r].size(); ++c) {
-                const int i = rounds[g][r][c];
-                const swiftly_b200_source& sr = sources[i];
-                SgSource& d = a.src[(size_t)g * slots + r * conc + c];
-                d.base = (const cplx*)sr.data;
-                d.ls = sr.line_stride;
-                d.es = sr.elem_stride;
-                if (sr.size == yN && yN != m) {  // window of a prepared facet line
-                    d.wbase = (int)pmod(yN / 2 - m / 2 + sc, yN);
-                    d.s_m = (int)pmod(sc, m);
-                    d.wmod = (int)yN;
-                } else {  // already a contribution
-                    d.wbase = 0;
-                    d.s_m = 0;
-                    d.wmod = (int)m;
-                }
-                const int64_t sf = floordiv(sr.facet_off * xM, h->N);
-                d.sf_m = (int)pmod(sf, m);
-                d.pos_base = pos_of[i];
-            }
+
+    // One launch carries at most SW_MAX_GROUPS groups and SW_MAX_SOURCES source slots (the
+    // descriptors travel as kernel parameters).  Larger jobs -- any number of facets, like
+    // the reference's sum_and_finish_subgrid (api_helper.py:73-112) -- are cut into pieces:
+    // whole groups are packed greedily; a single group with more rounds than fit is cut along
+    // its rounds, later pieces ADD their finished lines to the output (finishing is linear).
+    const int max_rounds_per_launch = SW_MAX_SOURCES / conc;
+    auto launch_piece = [&](int g0, int g1, size_t r0, size_t r1, bool accumulate) -> int {
+        const int ng = g1 - g0;
+        const int slots = (int)(r1 - r0) * conc;
+        SubgridAxisArgs a;
+        for (int i = 0; i < SW_MAX_SOURCES; ++i) {
+            a.src[i].base = nullptr;
+            a.src[i].ls = a.src[i].es = 0;
+            a.src[i].wbase = a.src[i].s_m = a.src[i].sf_m = a.src[i].pos_base = 0;
+            a.src[i].wmod = 1;
         }
+        a.first_round_tiles = (r0 == 0 && !accumulate && (int64_t)conc * m == xM) ? 1 : 0;
+        for (int g = g0; g < g1; ++g) {
+            const int64_t sc = floordiv(subgrid_offs[g] * yN, h->N);
+            const size_t rhi = r1 < rounds[g].size() ? r1 : rounds[g].size();
+            for (size_t r = r0; r < rhi; ++r) {
+                for (size_t c = 0; c < rounds[g][r].size(); ++c) {
+                    const int i = rounds[g][r][c];
+                    const swiftly_b200_source& sr = sources[i];
+                    SgSource& d = a.src[(size_t)(g - g0) * slots + (r - r0) * conc + c];
+                    d.base = (const cplx*)sr.data;
+                    d.ls = sr.line_stride;
+                    d.es = sr.elem_stride;
+                    if (sr.size == yN && yN != m) {  // window of a prepared facet line
+                        d.wbase = (int)pmod(yN / 2 - m / 2 + sc, yN);
+                        d.s_m = (int)pmod(sc, m);
+                        d.wmod = (int)yN;
+                    } else {  // already a contribution
+                        d.wbase = 0;
+                        d.s_m = 0;
+                        d.wmod = (int)m;
+                    }
+                    const int64_t sf = floordiv(sr.facet_off * xM, h->N);
+                    d.sf_m = (int)pmod(sf, m);
+                    d.pos_base = pos_of[i];
+                }
+            }
+            // the first round may store instead of accumulate when its windows tile the
+            // accumulator (conc disjoint windows of m samples with conc * m == xM)
+            if (rounds[g].size() <= r0 || (int)rounds[g][r0].size() != conc)
+                a.first_round_tiles = 0;
+        }
+        a.n_slots = slots;
+        a.n_groups = ng;
+        a.n_lines = out->n_lines;
+        a.out = (cplx*)out->data + (int64_t)g0 * out_group_stride;
+        a.out_ls = out->line_stride;
+        a.out_es = out->elem_stride;
+        a.out_gs = out_group_stride;
+        a.sz = (int)sz;
+        a.accumulate_out = accumulate ? 1 : 0;
+        for (int g = 0; g < SW_MAX_GROUPS; ++g) {
+            const int gg = g < ng ? g0 + g : g0;
+            a.start[g] = (int)pmod(xM / 2 - sz / 2 + subgrid_offs[gg], xM);
+            a.mask[g] = masks ? masks[gg] : nullptr;
+        }
+        return run_subgrid_axis(h, a, (cudaStream_t)stream);
+    };
+
+    int g0 = 0;
+    while (g0 < n_groups) {
+        size_t nr = rounds[g0].empty() ? 1 : rounds[g0].size();
+        if ((int)nr > max_rounds_per_launch) {
+            // one group, several launches along its rounds
+            for (size_t r0 = 0; r0 < nr; r0 += (size_t)max_rounds_per_launch) {
+                size_t r1 = r0 + (size_t)max_rounds_per_launch;
+                if (r1 > nr) r1 = nr;
+                SW_TRY(launch_piece(g0, g0 + 1, r0, r1, r0 > 0));
+            }
+            ++g0;
+            continue;
+        }
+        int g1 = g0 + 1;
+        while (g1 < n_groups && g1 - g0 < SW_MAX_GROUPS) {
+            size_t cand = rounds[g1].empty() ? 1 : rounds[g1].size();
+            size_t mx = cand > nr ? cand : nr;
+            if ((int)cand > max_rounds_per_launch ||
+                (int64_t)mx * conc * (g1 - g0 + 1) > SW_MAX_SOURCES)
+                break;
+            nr = mx;
+            ++g1;
+        }
+        SW_TRY(launch_piece(g0, g1, 0, nr, false));
+        g0 = g1;
     }
-    // does the first round of every group tile the accumulator (conc disjoint windows of m
-    // samples with conc * m == xM)?  Then it may store instead of accumulate.
-    a.first_round_tiles = ((int64_t)conc * m == xM) ? 1 : 0;
-    for (int g = 0; g < n_groups && a.first_round_tiles; ++g)
-        if (rounds[g].empty() || (int)rounds[g][0].size() != conc) a.first_round_tiles = 0;
-    a.n_slots = slots;
-    a.n_groups = n_groups;
-    a.n_lines = out->n_lines;
-    a.out = (cplx*)out->data;
-    a.out_ls = out->line_stride;
-    a.out_es = out->elem_stride;
-    a.out_gs = out_group_stride;
-    a.sz = (int)sz;
-    for (int g = 0; g < SW_MAX_GROUPS; ++g) {
-        const int gg = g < n_groups ? g : 0;
-        a.start[g] = (int)pmod(xM / 2 - sz / 2 + subgrid_offs[gg], xM);
-        a.mask[g] = masks ? masks[gg] : nullptr;
-    }
-    return run_subgrid_axis(h, a, (cudaStream_t)stream);
+    return SWIFTLY_B200_OK;
 }
 
 extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
@@ -171,16 +204,11 @@ extern "C" int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* h,
                                                     int64_t out_group_stride,
                                                     int64_t subgrid_off, const double* mask,
                                                     void* stream) {
-    if (n_groups < 1 || n_groups > SW_MAX_GROUPS)
-        return einval("sum_finish_axis: between 1 and " + std::to_string(SW_MAX_GROUPS) + " groups");
-    int64_t offs[SW_MAX_GROUPS];
-    const double* masks[SW_MAX_GROUPS];
-    for (int g = 0; g < n_groups; ++g) {
-        offs[g] = subgrid_off;
-        masks[g] = mask;
-    }
-    return sum_finish_groups(h, sources, group_sizes, n_groups, out, out_group_stride, offs, masks,
-                             stream);
+    if (n_groups < 1) return einval("sum_finish_axis: need at least one group");
+    std::vector<int64_t> offs((size_t)n_groups, subgrid_off);
+    std::vector<const double*> masks((size_t)n_groups, mask);
+    return sum_finish_groups(h, sources, group_sizes, n_groups, out, out_group_stride,
+                             offs.data(), masks.data(), stream);
 }
 
 // Groups that belong to DIFFERENT subgrids (a batch of the multi-GPU driver): per-group
@@ -239,7 +267,7 @@ extern "C" int swiftly_b200_extract_columns(const swiftly_b200* h, int n_facets,
         F.fb_off = (int)((yN - 1) / 2 - i.size / 2);
         F.pad_ = 0;
     }
-    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    SW_DEVICE_GUARD(h);
     const int64_t sc = floordiv(subgrid_off0 * yN, h->N);
     op.g.in = nullptr;
     op.g.out = nullptr;
@@ -285,7 +313,7 @@ extern "C" int swiftly_b200_subgrid_to_facets(const swiftly_b200* h, int n_facet
         F.sf_m = (int)pmod(sf, m);
         F.base_x = (int)pmod(xM / 2 - m / 2 + sf, xM);
     }
-    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    SW_DEVICE_GUARD(h);
     const int64_t sc = floordiv(subgrid_off1 * yN, h->N);
     op.g.in = nullptr;
     op.g.out = nullptr;
@@ -334,7 +362,7 @@ extern "C" int swiftly_b200_fold_column(const swiftly_b200* h, int n_facets,
         F.fb_off = (int)((yN - 1) / 2 - o.size / 2);
         F.pad_ = 0;
     }
-    SW_CUDA(cudaSetDevice(h->device), "cudaSetDevice");
+    SW_DEVICE_GUARD(h);
     const int64_t sc = floordiv(subgrid_off0 * yN, h->N);
     op.g.in = nullptr;
     op.g.out = nullptr;

@@ -18,7 +18,35 @@ inline int64_t floordiv(int64_t a, int64_t b) {  // python // for b > 0
     return q;
 }
 
+// Make the plan's device current for the duration of a call and restore the caller's
+// device afterwards (also from swiftly_b200_destroy, which may run at arbitrary GC time):
+// a process that drives several GPUs must not find its current device changed by a
+// library call.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) {
+            prev = -1;
+            return;
+        }
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    bool ok() const { return err == cudaSuccess; }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 }  // namespace swiftly
+
+#define SW_DEVICE_GUARD(h)                                                        \
+    swiftly::DeviceGuard device_guard__((h)->device);                             \
+    if (!device_guard__.ok()) return swiftly::cuda_fail(device_guard__.err, "cudaSetDevice")
 
 #define SW_CUDA(call, what)                                           \
     do {                                                              \

@@ -15,6 +15,7 @@
 #if defined(SWIFTLY_EMU)
 #include "emu_runtime.h"
 #else
+#include <cuda.h>
 #include <cuda_runtime.h>
 #endif
 
@@ -98,6 +99,23 @@ SW_HD int64_t pmod(int64_t a, int64_t n) {
     return r < 0 ? r + n : r;
 }
 
+// Descriptor of a strided global tile for the TMA engine: rank 4, dimension 0 = (re, im) of a
+// complex128 sample, dimensions 1..3 = line / sample / group of an output array in ascending
+// stride order.  On the device this is the driver's opaque CUtensorMap (made by
+// cuTensorMapEncodeTiled, capi_util.h); the host-emulated test build keeps the plain numbers.
+#if defined(SWIFTLY_EMU)
+struct TensorMap4 {
+    double* base;
+    int64_t stride[4];  // in doubles
+    int64_t dim[4];
+    int box[4];
+};
+#else
+struct alignas(64) TensorMap4 {
+    CUtensorMap map;
+};
+#endif
+
 #if defined(__CUDACC__) && !defined(SWIFTLY_EMU)
 // Execution context on the device: one CTA.
 struct DeviceCtx {
@@ -107,6 +125,68 @@ struct DeviceCtx {
     // named barrier over `count` threads (a multiple of 32; whole warps), id 1..15
     __device__ __forceinline__ void group_sync(int id, int count) const {
         asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+    }
+    // non-blocking arrival at a named barrier (producer side of a bar.sync / bar.arrive pair)
+    __device__ __forceinline__ void group_arrive(int id, int count) const {
+        asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+    }
+    // ---- bulk asynchronous copies (TMA engine, cp.async.bulk) tracked by an mbarrier ----
+    // `bar` is an 8-byte shared-memory word; one thread initialises it (count 1 = the thread
+    // that issues the copies), everybody waits on its phase parity.
+    __device__ __forceinline__ void tx_init(uint64_t* bar) const {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // announce `bytes` of bulk copies for the current phase (issuing thread only)
+    __device__ __forceinline__ void tx_expect(uint64_t* bar, uint32_t bytes) const {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+    }
+    // global -> shared bulk copy (16-byte aligned, size a multiple of 16) completing on `bar`
+    __device__ __forceinline__ void tx_copy(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) const {
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+              "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+    }
+    __device__ __forceinline__ void tx_wait(uint64_t* bar, uint32_t parity) const {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    }
+    // ---- bulk tensor stores (TMA): shared memory tile -> strided global tile ----
+    // ordinary shared-memory writes become visible to the asynchronous proxy
+    __device__ __forceinline__ void fence_async() const {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // store the box at coordinates (0, c1, c2, c3) of a rank-4 tensor map (dimension 0 = the
+    // two doubles of a complex sample) from a dense shared-memory tile
+    __device__ __forceinline__ void tensor_store(const void* map, const void* smem_src, int c1,
+                                                 int c2, int c3) const {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+            ::"l"(map), "r"(0), "r"(c1), "r"(c2), "r"(c3),
+              "r"((uint32_t)__cvta_generic_to_shared(smem_src)) : "memory");
+    }
+    __device__ __forceinline__ void bulk_commit() const {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // the bulk stores this thread committed have finished READING shared memory
+    __device__ __forceinline__ void bulk_wait_read() const {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    // bulk L2 prefetch of a contiguous global region (no registers, no LSU wavefronts)
+    __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) const {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes)
+                     : "memory");
     }
 };
 
@@ -119,7 +199,8 @@ struct MinBlocks {
 };
 
 template <class Body>
-__global__ void __launch_bounds__(Body::THREADS, MinBlocks<Body>::V) kernel_entry(const Body body) {
+__global__ void __launch_bounds__(Body::THREADS, MinBlocks<Body>::V)
+    kernel_entry(const __grid_constant__ Body body) {
     DeviceCtx ctx;
     ctx.tid = threadIdx.x;
     ctx.bid = blockIdx.x;

@@ -1,11 +1,79 @@
 // SwiFTly B200 -- size dispatch of extract_columns (one translation unit per primitive keeps
 // the heavy FP64 template instantiations compiling in parallel).
 #include "dispatch.cuh"
+#include "extract_tma.cuh"
 
 namespace swiftly {
 
+// TMA-staged K2 (extract_tma.cuh): persistent CTAs, the facet row of the next line is copied
+// into shared memory by the bulk-copy engine while the current line is transformed
+template <int H, bool SPLIT>
+static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, int max_fs,
+                              cudaStream_t s) {
+    typedef ExtractColumnsTmaKernel<H, SPLIT> K;
+    K k;
+    k.op = op;
+    k.tw = twiddles(h, H);
+    k.tw2 = SPLIT ? twiddles_full(h, 2 * H) : nullptr;
+    if (!k.tw || (SPLIT && !k.tw2)) return SWIFTLY_B200_ECUDA;
+    k.in_cap = (max_fs + 1) & ~1;
+    const size_t smem = K::smem_bytes(k.in_cap);
+    int per_sm = (int)((size_t)227 * 1024 / smem);
+    if (per_sm > 512 / K::THREADS) per_sm = 512 / K::THREADS;
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)148 * per_sm;
+    if (blocks > op.g.n_lines) blocks = op.g.n_lines;
+    k.scratch = nullptr;
+    if (SPLIT) {
+        k.scratch = split_scratch(h, s, (size_t)blocks * H);
+        if (!k.scratch) return SWIFTLY_B200_ECUDA;
+    }
+    cudaError_t e = launch_body(k, (int)blocks, smem, s);
+    return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "extract_columns (TMA) kernel launch");
+}
+
+// returns -1 when the TMA-staged kernel does not apply (then the generic kernels run)
+static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cudaStream_t s) {
+    const int n = op.n;
+    const int n_facets = (int)(op.g.n_lines / op.lines_per);
+    int max_fs = 0;
+    for (int f = 0; f < n_facets; ++f) {
+        if (op.fac[f].fs > max_fs) max_fs = op.fac[f].fs;
+        if (op.fac[f].fs < 1) return -1;
+    }
+    const bool split = n > MAX_DIRECT_FFT || h->force_split;
+    const int hh = split ? n / 2 : n;
+    // staging buffer + exchange buffer must fit the 227 KiB of one SM
+    if ((size_t)((max_fs + 1) & ~1) * 16 + (size_t)(hh + hh / 16) * 8 + 16 > (size_t)227 * 1024)
+        return -1;
+    if (split) {
+        switch (n) {
+            case 16384: return launch_extract_tma<8192, true>(h, op, max_fs, s);
+#if defined(SWIFTLY_EMU)
+            case 512: return launch_extract_tma<256, true>(h, op, max_fs, s);
+#endif
+            default: return -1;
+        }
+    }
+    switch (n) {
+#if defined(SWIFTLY_EMU)
+        case 128: return launch_extract_tma<128, false>(h, op, max_fs, s);
+        case 512: return launch_extract_tma<512, false>(h, op, max_fs, s);
+#endif
+        case 1024: return launch_extract_tma<1024, false>(h, op, max_fs, s);
+        case 2048: return launch_extract_tma<2048, false>(h, op, max_fs, s);
+        case 4096: return launch_extract_tma<4096, false>(h, op, max_fs, s);
+        case 8192: return launch_extract_tma<8192, false>(h, op, max_fs, s);
+        default: return -1;
+    }
+}
+
 int run_extract_columns(const swiftly_b200* h, const ExtractColumnsOp& op, bool lf, cudaStream_t s) {
     const int n = op.n;
+    if (h->sg_variant != 4 && h->sg_variant != 3) {  // 4: round-1 kernels (debug hook)
+        int rc = try_extract_tma(h, op, s);
+        if (rc != -1) return rc;
+    }
     if (h->force_split && n >= 2 * MIN_FFT && n <= MAX_DIRECT_FFT) {
         switch (n) {
 #if defined(SWIFTLY_EMU)
@@ -15,6 +83,8 @@ int run_extract_columns(const swiftly_b200* h, const ExtractColumnsOp& op, bool 
             default: break;
         }
     }
+    if (h->sg_variant == 3 && n == 16384)  // experiment: 4 x 4096 split, 256-thread CTAs
+        return launch_split_f<4096, +1, ExtractColumnsOp>(h, op, 4, s);
     switch (n) {
         SW_DIRECT_CASES(+1, ExtractColumnsOp)
         case 16384: return launch_split<8192, +1, ExtractColumnsOp>(h, op, s);

@@ -1,5 +1,6 @@
 // SwiFTly B200 -- dispatch of the fused subgrid axis kernel over (m, xM) pairs.
 #include "dispatch.cuh"
+#include "subgrid_pp.cuh"
 
 namespace swiftly {
 
@@ -25,9 +26,71 @@ static int launch_sg_axis_l(const swiftly_b200* h, const SubgridAxisArgs& a, cud
     }
     k.scale = 1.0 / (double)XM;
     k.first_round_tiles = a.first_round_tiles;
+    k.accumulate_out = a.accumulate_out;
     cudaError_t e = launch_body(k, grid_for(((a.n_lines + LINES - 1) / LINES) * a.n_groups, 1), k.SMEM, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "subgrid axis kernel launch");
 }
+
+// ping-pong variant: two thread groups (two lines) per CTA, LSU token between them
+template <int M, int XM, bool TOKENS>
+static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cudaStream_t s) {
+    SubgridAxisKernelPP<M, XM, TOKENS> k;
+    for (int i = 0; i < SW_MAX_SOURCES; ++i) k.src[i] = a.src[i];
+    k.n_slots = a.n_slots;
+    k.n_groups = a.n_groups;
+    k.fn = h->d_Fn;
+    k.tw_m = twiddles(h, M);
+    k.tw_x = twiddles(h, XM);
+    if (!k.tw_m || !k.tw_x) return SWIFTLY_B200_ECUDA;
+    k.n_lines = a.n_lines;
+    k.out = a.out;
+    k.out_ls = a.out_ls;
+    k.out_es = a.out_es;
+    k.out_gs = a.out_gs;
+    k.sz = a.sz;
+    for (int g = 0; g < SW_MAX_GROUPS; ++g) {
+        k.start[g] = a.start[g];
+        k.mask[g] = a.mask[g];
+    }
+    k.scale = 1.0 / (double)XM;
+    k.first_round_tiles = a.first_round_tiles;
+    k.accumulate_out = a.accumulate_out;
+    // finished lines through the TMA engine when the staging buffer (the work area) holds a
+    // line and the output can be described by a tensor map; sg_variant 5: direct stores
+    k.tma_out = 0;
+    k.tma_box = a.sz < 256 ? a.sz : 256;
+    k.tma_slot_line = k.tma_slot_elem = k.tma_slot_group = 1;
+    // (the last box may be partial: the engine still reads a whole box from shared memory)
+    const size_t staged = (size_t)((a.sz + k.tma_box - 1) / (k.tma_box > 0 ? k.tma_box : 1)) *
+                          (size_t)k.tma_box * sizeof(cplx);
+    if (!a.accumulate_out && h->sg_variant != 5 && a.sz >= 1 &&
+        staged <= (size_t)k.WORK * sizeof(double)) {
+        int slot[3];
+        if (make_out_map(&k.out_map, a.out, a.out_ls, a.out_es, a.out_gs, a.n_lines, a.sz,
+                         a.n_groups, k.tma_box, slot)) {
+            k.tma_out = 1;
+            k.tma_slot_line = slot[0];
+            k.tma_slot_elem = slot[1];
+            k.tma_slot_group = slot[2];
+        }
+    }
+    // persistent: one CTA per SM, every CTA walks over line pairs
+    int64_t pairs = ((a.n_lines + 1) / 2) * a.n_groups;
+    int grid = (int)(pairs < 148 ? pairs : 148);
+    cudaError_t e = launch_body(k, grid, k.SMEM, s);
+    return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "subgrid axis (ping-pong) kernel launch");
+}
+
+template <int M, int XM>
+struct PingPongFits {
+#if defined(SWIFTLY_EMU)
+    static constexpr bool V = (XM / M) <= 4;
+#else
+    static constexpr bool V = (XM / M) <= 4 && (XM / 16) % 32 == 0 &&
+                              2 * ((size_t)(XM + XM / 16) * 16 + (size_t)(XM + XM / 16 + 8) * 8) <=
+                                  227 * 1024;
+#endif
+};
 
 // two adjacent lines per CTA when every source and the output have unit line stride
 template <int M, int XM>
@@ -35,6 +98,13 @@ static int launch_sg_axis(const swiftly_b200* h, const SubgridAxisArgs& a, cudaS
     bool adjacent = a.out_ls == 1 && a.n_lines > 1;
     for (int i = 0; i < SW_MAX_SOURCES && adjacent; ++i)
         if (a.src[i].base && a.src[i].ls != 1) adjacent = false;
+    if constexpr (PingPongFits<M, XM>::V) {
+        // sg_variant (debug hook): 0 = ping-pong with tokens, 1 = round-1 kernel,
+        // 2 = ping-pong layout without tokens
+        if (!adjacent && h->sg_variant != 1)
+            return h->sg_variant == 2 ? launch_sg_axis_pp<M, XM, false>(h, a, s)
+                                      : launch_sg_axis_pp<M, XM, true>(h, a, s);
+    }
     // 2 lines need 2 x (acc + work) of shared memory: only the pairs that fit
     if constexpr (2 * ((size_t)(XM + 4) * sizeof(cplx) + (size_t)(XM + XM / 16 + 40) * 8) <=
                   227 * 1024) {

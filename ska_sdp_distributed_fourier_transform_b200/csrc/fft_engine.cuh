@@ -27,9 +27,23 @@
 // is folded into the loader (split2_*), see kernels.cuh.
 #pragma once
 
+#include <type_traits>
+#include <utility>
+
 #include "common.cuh"
 
 namespace swiftly {
+
+// A Sync object is a callable CTA (or thread-group) barrier.  It may additionally offer
+// acquire() / release(): hooks around the shared-memory exchange of every pass.  The
+// ping-pong kernels (subgrid_pp.cuh) use them to hand an "LSU token" back and forth between
+// two thread groups of one CTA, so that one group moves data through shared memory (LSU
+// bound) exactly while the other one runs its butterflies (FP64 bound).  acquire() must be
+// at least as strong as the barrier itself (everybody of the transform has arrived).
+template <class S, class = void>
+struct HasPhaseHooks : std::false_type {};
+template <class S>
+struct HasPhaseHooks<S, std::void_t<decltype(std::declval<S&>().acquire())>> : std::true_type {};
 
 // ---------------------------------------------------------------- radix kernels
 // v * (c + i * DIR * s)
@@ -225,7 +239,9 @@ SW_HD void stockham_tail(int lt, double* sm, const cplx* tw, cplx* v, St& st, Sy
     constexpr int NB = N / R;
     constexpr int ITERS = 16 / R;
     constexpr bool LAST = (NS * R == N);
+    constexpr bool HOOKS = HasPhaseHooks<Sync>::value;
     double nx[16];
+    if constexpr (HOOKS) sync.acquire();
 #pragma unroll
     for (int it = 0; it < ITP; ++it) {
         const int j = lt + it * T;
@@ -255,6 +271,7 @@ SW_HD void stockham_tail(int lt, double* sm, const cplx* tw, cplx* v, St& st, Sy
 #pragma unroll
         for (int r = 0; r < R; ++r) v[it * R + r] = mk(nx[it * R + r], sm[sm_phys(j + r * NB)]);
     }
+    if constexpr (HOOKS) sync.release();
     // twiddle + butterflies of this pass
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -274,8 +291,63 @@ SW_HD void stockham_tail(int lt, double* sm, const cplx* tw, cplx* v, St& st, Sy
             for (int r = 0; r < R; ++r) st(base + r * NS, v[it * R + r]);
         }
     } else {
-        sync();  // everybody has read the imaginary parts before the buffer is rewritten
+        // everybody has read the imaginary parts before the buffer is rewritten (with hooks
+        // the acquire() of the next pass is that barrier)
+        if constexpr (!HOOKS) sync();
         stockham_tail<N, NS * R, R, DIR>(lt, sm, tw, v, st, sync);
+    }
+}
+
+// Same passes with a COMPLEX exchange buffer (N + N/16 cplx): one trip (16-byte accesses)
+// and two barriers per pass instead of two trips and four barriers; twice the footprint.
+// 16-byte accesses are served per quarter warp; the pad per 16 keeps the stride-16 scatter
+// on 8 distinct 16-byte bank groups.
+template <int N, int NS, int RP, int DIR, class St, class Sync>
+SW_HD void stockham_tail_cx(int lt, cplx* sm, const cplx* tw, cplx* v, St& st, Sync& sync) {
+    constexpr int T = FftCfg<N>::T;
+    constexpr int NSP = NS / RP;
+    constexpr int ITP = 16 / RP;
+    constexpr int R = PassRadix<N, NS>::R;
+    constexpr int NB = N / R;
+    constexpr int ITERS = 16 / R;
+    constexpr bool LAST = (NS * R == N);
+    constexpr bool HOOKS = HasPhaseHooks<Sync>::value;
+    if constexpr (HOOKS) sync.acquire();
+#pragma unroll
+    for (int it = 0; it < ITP; ++it) {
+        const int j = lt + it * T;
+        const int base = (j / NSP) * NS + (j & (NSP - 1));
+#pragma unroll
+        for (int r = 0; r < RP; ++r) sm[sm_phys(base + r * NSP)] = v[it * RP + r];
+    }
+    sync();
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = lt + it * T;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[it * R + r] = sm[sm_phys(j + r * NB)];
+    }
+    if constexpr (HOOKS) sync.release();
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int j = lt + it * T;
+        const int k = j & (NS - 1);
+        cplx w1 = ldg_c(tw + TwOffset<NS>::V + k);
+        if (DIR > 0) w1.y = -w1.y;
+        TwiddlePowers<R>::apply(v + it * R, w1);
+        Radix<R, DIR>::run(v + it * R);
+    }
+    if constexpr (LAST) {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int j = lt + it * T;
+            const int base = (j / NS) * (NS * R) + (j & (NS - 1));
+#pragma unroll
+            for (int r = 0; r < R; ++r) st(base + r * NS, v[it * R + r]);
+        }
+    } else {
+        if constexpr (!HOOKS) sync();
+        stockham_tail_cx<N, NS * R, R, DIR>(lt, sm, tw, v, st, sync);
     }
 }
 
@@ -304,6 +376,26 @@ SW_HD void line_fft(int lt, double* sm, const cplx* tw, Ld& ld, St& st, Sync& sy
         stockham_tail<N, R, R, DIR>(lt, sm, tw, v, st, sync);
     }
     (void)T;
+}
+
+}  // namespace swiftly
+
+namespace swiftly {
+
+// line_fft with the complex exchange buffer.  ALIAS: the loader reads from the exchange
+// buffer's own memory (an accumulator that turns into the exchange buffer): everybody must
+// have loaded before the first exchange writes, which costs one extra barrier.
+template <int N, int DIR, bool ALIAS, class Ld, class St, class Sync>
+SW_HD void line_fft_cx(int lt, cplx* sm, const cplx* tw, Ld& ld, St& st, Sync& sync) {
+    constexpr int R = PassRadix<N, 1>::R;  // 16
+    constexpr int NB = N / R;
+    static_assert(N > 16, "complex-exchange variant is for multi-pass transforms");
+    cplx v[16];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = ld(lt + r * NB);
+    if constexpr (ALIAS && !HasPhaseHooks<Sync>::value) sync();
+    Radix<R, DIR>::run(v);
+    stockham_tail_cx<N, R, R, DIR>(lt, sm, tw, v, st, sync);
 }
 
 }  // namespace swiftly

@@ -612,6 +612,9 @@ struct SubgridAxisKernel {
     // disjoint and tile the accumulator completely (the regular facet layouts): the first
     // round then stores instead of read-modify-write and the accumulator is not zeroed
     int first_round_tiles;
+    // the launch is a later piece of a job with more sources than fit one launch: the
+    // finished lines are ADDED to `out` (finishing is linear)
+    int accumulate_out;
 
     template <class Ctx>
     SW_HD void operator()(Ctx& ctx) const {
@@ -713,7 +716,13 @@ struct SubgridAxisKernel {
                     int r = wrap_sub(pc, gstart, XM);
                     if (line_ok && r < sz) {
                         double f = gmask ? scale * ldg_d(gmask + r) : scale;
-                        st_stream(o + (int64_t)r * out_es, cscale(v, f));
+                        cplx* dst = o + (int64_t)r * out_es;
+                        if (accumulate_out) {
+                            cplx a = *dst;
+                            *dst = mk(a.x + f * v.x, a.y + f * v.y);
+                        } else {
+                            st_stream(dst, cscale(v, f));
+                        }
                     }
                 };
                 line_fft<XM, +1>(t, work, tw_x, ld, st, sync);

@@ -21,6 +21,7 @@ struct swiftly_b200 {
     // scratch lines of the split (2 x n/2) kernels, one buffer per stream: (pointer, samples)
     mutable std::map<cudaStream_t, std::pair<swiftly::cplx*, size_t>> scratch;
     int force_split;  // debug / test: transform yN lines with the 2 x yN/2 split path
+    int sg_variant;   // debug / test: fused subgrid kernel variant (dispatch_subgrid_axis.cu)
 };
 
 namespace swiftly {
@@ -66,7 +67,13 @@ struct SubgridAxisArgs {
     int start[SW_MAX_GROUPS];
     const double* mask[SW_MAX_GROUPS];
     int first_round_tiles;
+    int accumulate_out;  // add to `out` instead of overwriting it (later pieces of a split job)
 };
+// rank-4 tensor map over an output array with arbitrary line / sample / group strides
+// (tensor_map.cu); slot[0..2] receive the coordinate slots of line / sample / group
+bool make_out_map(TensorMap4* tm, cplx* out, int64_t out_ls, int64_t out_es, int64_t out_gs,
+                  int64_t n_lines, int64_t sz, int64_t n_groups, int box_rows, int* slot);
+
 // returns SWIFTLY_B200_EUNSUPPORTED (without setting up anything) when the (m, xM) pair has no
 // fused instantiation; conc_out receives the number of sources processed concurrently
 int subgrid_axis_conc(int m, int xM);

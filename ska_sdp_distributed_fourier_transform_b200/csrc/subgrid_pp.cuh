@@ -1,0 +1,220 @@
+// SwiFTly B200 -- ping-pong variant of the fused subgrid axis kernel.
+//
+// Same mathematics and the same parameters as SubgridAxisKernel (kernels.cuh): for every
+// output line the m-point transforms of the sources are overlap-added (Fn weighted) into an
+// xM accumulator in shared memory, the xM-point inverse transform runs from there and the
+// wanted xA samples are stored (api_helper.py:73-112, core.py:224-325).
+//
+// What is different is how an SM is kept busy.  A line alternates between shared-memory
+// exchange phases (LSU bound) and butterfly phases (FP64 bound).  With independent CTAs
+// the two co-resident lines of an SM fall into lockstep -- both exchange, then both compute
+// -- and each pipe idles while the other one works (round 1: LSU 60 % + FP64 39 % of the
+// time).  Here ONE CTA holds two thread groups, each with its own line, its own accumulator
+// and exchange buffers, and the groups pass an "LSU token" through a pair of named barriers
+// (bar.sync / bar.arrive): a group runs an exchange phase only while it holds the token and
+// hands it over when the phase ends, so the groups are forced into anti-phase -- group 0
+// moves data while group 1 multiplies, and vice versa.
+//
+// The xM-point transform exchanges COMPLEX samples (one trip per pass, two barriers) through
+// the accumulator's own storage: the accumulator is dead once the first pass has loaded it.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace swiftly {
+
+template <int M, int XM, bool TOKENS>
+struct SubgridAxisKernelPP {
+    static constexpr int T_M = FftCfg<M>::T;
+    static constexpr int T_X = FftCfg<XM>::T;
+    static constexpr int GROUPS = 2;
+    static constexpr int THREADS = T_X * GROUPS;
+    static constexpr int CONC = T_X / T_M;  // concurrent m-point transforms per line
+    static_assert(CONC >= 1 && CONC <= 4, "at most four concurrent m-point transforms");
+    static constexpr int WSTRIDE = FftCfg<M>::PADDED | 1;
+    static constexpr int WORK = (CONC * WSTRIDE + 1) & ~1;  // doubles per group
+    static constexpr int ACCS = XM + XM / 16;  // cplx per group: accumulator / xM exchange
+    static constexpr size_t SMEM =
+        (size_t)GROUPS * ((size_t)ACCS * sizeof(cplx) + (size_t)WORK * sizeof(double));
+#if !defined(SWIFTLY_EMU)
+    static_assert(T_X % 32 == 0, "a thread group must be whole warps");
+#endif
+    // named barriers need whole warps; smaller transforms use the group barrier
+    static constexpr bool SUB_BARRIERS = (T_M % 32 == 0) && CONC > 1;
+
+    // identical to SubgridAxisKernel
+    SgSource src[SW_MAX_SOURCES];
+    int n_slots;
+    int n_groups;
+    const double* fn;
+    const cplx* tw_m;
+    const cplx* tw_x;
+    int64_t n_lines;
+    cplx* out;
+    int64_t out_ls, out_es, out_gs;
+    int sz;
+    int start[SW_MAX_GROUPS];
+    const double* mask[SW_MAX_GROUPS];
+    double scale;
+    int first_round_tiles;
+    int accumulate_out;
+    // finished lines leave through the TMA engine: staged in the (idle) work buffer, then
+    // bulk tensor stores scatter them with the output's strides
+    int tma_out;
+    int tma_box;                                       // samples per bulk tensor store
+    int tma_slot_line, tma_slot_elem, tma_slot_group;  // coordinate slots (1..3)
+    TensorMap4 out_map;
+
+    // barrier ids: 0 = whole CTA, 1 + g = group g, 3 + g * CONC + c = transform c of group g,
+    // 11 + g = token of group g
+    template <class Ctx>
+    struct GroupSync {
+        const Ctx& ctx;
+        int bar_id, bar_count;  // barrier of the threads that share the exchange buffer
+        int grp;
+        SW_HD void operator()() const { ctx.group_sync(bar_id, bar_count); }
+        // start of an exchange phase: wait for the token (the other group's release); the
+        // wait is also a barrier over the whole group
+        SW_HD void acquire() const {
+            if (TOKENS)
+                ctx.group_sync(11 + grp, THREADS);
+            else
+                ctx.group_sync(bar_id, bar_count);
+        }
+        SW_HD void release() const {
+            if (TOKENS) ctx.group_arrive(11 + (1 - grp), THREADS);
+        }
+    };
+
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        const int grp = ctx.tid / T_X;  // thread group = which of the CTA's two lines
+        const int t = ctx.tid % T_X;    // thread within the group
+        cplx* acc = (cplx*)ctx.smem + (size_t)grp * ACCS;
+        double* work = (double*)((cplx*)ctx.smem + (size_t)GROUPS * ACCS) + (size_t)grp * WORK;
+        const int c = t / T_M;
+        const int lt = t % T_M;
+        GroupSync<Ctx> gsync{ctx, 1 + grp, T_X, grp};
+        GroupSync<Ctx> msync{ctx, SUB_BARRIERS ? 3 + grp * CONC + c : 1 + grp,
+                             SUB_BARRIERS ? T_M : T_X, grp};
+        // group 1 hands the token to group 0 to start with
+        if (TOKENS && grp == 1) ctx.group_arrive(11, THREADS);
+        const int64_t pairs = (n_lines + GROUPS - 1) / GROUPS;  // line pairs per source group
+        const int64_t total = pairs * n_groups;
+        for (int64_t gl = ctx.bid; gl < total; gl += ctx.nblocks) {
+            const int sgrp = (int)(gl / pairs);
+            const int64_t line = (gl - (int64_t)sgrp * pairs) * GROUPS + grp;
+            const bool line_ok = line < n_lines;
+            if (tma_out) {
+                // the previous line's bulk stores must have read the staging (= work) buffer
+                if (t == 0) ctx.bulk_wait_read();
+                gsync();
+            }
+            if (!first_round_tiles) {
+                for (int i = t; i < XM; i += T_X) acc[i] = mk(0.0, 0.0);
+                gsync();
+            }
+            for (int slot0 = 0; slot0 < n_slots; slot0 += CONC) {
+                const bool overwrite = first_round_tiles && slot0 == 0;
+                const int slot = sgrp * n_slots + slot0 + c;
+                const bool active = line_ok && slot0 + c < n_slots && src[slot].base != nullptr;
+                const cplx* base = active ? src[slot].base + line * src[slot].ls : nullptr;
+                const int64_t es = active ? src[slot].es : 0;
+                const int wbase = active ? src[slot].wbase : 0;
+                const int s_m = active ? src[slot].s_m : 0;
+                const int wmod = active ? src[slot].wmod : 1;
+                const int sf_m = active ? src[slot].sf_m : 0;
+                const int pos_base = active ? src[slot].pos_base : 0;
+                auto ld = [&](int q) {
+                    if (!active) return mk(0.0, 0.0);
+                    int tc = wrap_add(q, M / 2, M);
+                    int idx = wrap_add(wbase, wrap_sub(tc, s_m, M), wmod);
+                    return ld_stream(base + (int64_t)idx * es);
+                };
+                auto st = [&](int w, cplx v) {
+                    if (!active) return;
+                    int wc = wrap_add(w, M / 2, M);
+                    int u = wrap_sub(wc, sf_m, M);
+                    int pos = wrap_add(pos_base, u, XM);
+                    double f = ldg_d(fn + u);
+                    if (overwrite) {
+                        acc[pos] = mk(f * v.x, f * v.y);
+                    } else {
+                        cplx a = acc[pos];
+                        acc[pos] = mk(a.x + f * v.x, a.y + f * v.y);
+                    }
+                };
+                // L2 prefetch of what this thread loads next: the next round of this line, or
+                // the first round of the group's next line
+                {
+                    int pslot0 = slot0 + CONC, psgrp = sgrp;
+                    int64_t pline = line;
+                    if (pslot0 >= n_slots) {
+                        pslot0 = 0;
+                        const int64_t ngl = gl + ctx.nblocks;
+                        psgrp = (int)(ngl / pairs);
+                        pline = (ngl - (int64_t)psgrp * pairs) * GROUPS + grp;
+                        if (ngl >= total || pline >= n_lines) psgrp = -1;
+                    }
+                    if (psgrp >= 0 && pslot0 + c < n_slots) {
+                        const SgSource& ps = src[psgrp * n_slots + pslot0 + c];
+                        if (ps.base != nullptr && ps.es == 1) {
+                            const cplx* pb = ps.base + pline * ps.ls;
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                int tc = wrap_add(lt + r * T_M, M / 2, M);
+                                int idx = wrap_add(ps.wbase, wrap_sub(tc, ps.s_m, M), ps.wmod);
+                                prefetch_l2(pb + (int64_t)idx * ps.es);
+                            }
+                        }
+                    }
+                }
+                line_fft<M, -1>(lt, work + (size_t)c * WSTRIDE, tw_m, ld, st, msync);
+                gsync();  // accumulator complete; work buffers free
+            }
+            {
+                cplx* o = out + (int64_t)sgrp * out_gs + line * out_ls;
+                const int gstart = start[sgrp];
+                const double* gmask = mask[sgrp];
+                auto ld = [&](int q) { return acc[wrap_add(q, XM / 2, XM)]; };
+                cplx* stage = (cplx*)work;
+                auto st = [&](int p, cplx v) {
+                    int pc = wrap_add(p, XM / 2, XM);
+                    int r = wrap_sub(pc, gstart, XM);
+                    if (line_ok && r < sz) {
+                        double f = gmask ? scale * ldg_d(gmask + r) : scale;
+                        cplx* dst = o + (int64_t)r * out_es;
+                        if (tma_out) {
+                            stage[r] = cscale(v, f);
+                        } else if (accumulate_out) {
+                            cplx a = *dst;
+                            *dst = mk(a.x + f * v.x, a.y + f * v.y);
+                        } else {
+                            st_stream(dst, cscale(v, f));
+                        }
+                    }
+                };
+                // the exchange buffer IS the accumulator: the acquire() (a group barrier) of
+                // the first pass comes after every thread's loads
+                line_fft_cx<XM, +1, true>(t, acc, tw_x, ld, st, gsync);
+            }
+            gsync();  // accumulator is rewritten by the next line; staged line complete
+            if (tma_out && t == 0 && line_ok) {
+                ctx.fence_async();
+                int c[4] = {0, 0, 0, 0};
+                c[tma_slot_line] = (int)line;
+                c[tma_slot_group] = sgrp;
+                for (int r0 = 0; r0 < sz; r0 += tma_box) {
+                    c[tma_slot_elem] = r0;
+                    ctx.tensor_store(&out_map, (const cplx*)work + r0, c[1], c[2], c[3]);
+                }
+                ctx.bulk_commit();
+            }
+        }
+        if (tma_out && t == 0) ctx.bulk_wait_read();
+        // consume group 1's last release so that every barrier ends balanced
+        if (TOKENS && grp == 0) ctx.group_sync(11, THREADS);
+    }
+};
+
+}  // namespace swiftly

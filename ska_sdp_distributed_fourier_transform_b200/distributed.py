@@ -135,7 +135,7 @@ class SwiftlyForwardSharded:
         st = self._symm
         if xA not in st["slots"]:
             m = self.core.xM_yN_size
-            shape = (2, self.world, self.rows_max, m, xA)
+            shape = (2, self.world, self.rows_max, xA, m)  # strips transposed, see api.py
             n = 1
             for d in shape:
                 n *= d
@@ -145,7 +145,7 @@ class SwiftlyForwardSharded:
             views = []
             for r in range(self.world):
                 peer = hdl.get_buffer(r, (2 * n,), torch.float64, 0)
-                views.append(torch.view_as_complex(peer.view(n, 2)).view(shape))
+                views.append(torch.view_as_complex(peer.view(n, 2)).view(shape).transpose(3, 4))
             st["slots"][xA] = (hdl, views, buf)
         return st["slots"][xA]
 
@@ -182,10 +182,12 @@ class SwiftlyForwardSharded:
         key = (slot, xA)
         if key not in self._bufs:
             m = self.core.xM_yN_size
-            shape = (self.world, self.rows_max, m, xA)
+            # strips are stored transposed (contribution index contiguous, see api.py)
+            shape = (self.world, self.rows_max, xA, m)
             send = torch.zeros(shape, dtype=torch.complex128, device=self.device)
             recv = torch.zeros(shape, dtype=torch.complex128, device=self.device)
-            self._bufs[key] = (send, recv)
+            # (logical (world, row, m, xA) views for the kernels, flat storage for the exchange)
+            self._bufs[key] = (send.transpose(2, 3), recv.transpose(2, 3), send, recv)
         return self._bufs[key]
 
     def _local_strips(self, sg, out):
@@ -207,12 +209,12 @@ class SwiftlyForwardSharded:
 
         Subgrids that share the subgrid column (``off0``) go into ONE kernel launch (groups =
         subgrids x local facet rows, per-group subgrid offset and mask)."""
-        max_groups = 16
         b = 0
         while b < len(batch):
-            e = b
+            # the C side cuts a launch that carries more groups / sources than the kernel
+            # parameters hold into several launches, so a run is only bounded by the column
+            e = b + 1
             while (e < len(batch) and batch[e].off0 == batch[b].off0
-                   and (e - b + 1) * max(1, len(self.my_rows)) <= max_groups
                    and batch[e].size == batch[b].size):
                 e += 1
             if not self.my_rows:
@@ -290,13 +292,13 @@ class SwiftlyForwardSharded:
                     results[idx] = DeviceTask(out)
 
         for bi, batch in enumerate(batches):
-            send, recv = self._buffers(bi % 2, xA)
+            send, recv, send_flat, recv_flat = self._buffers(bi % 2, xA)
             self._local_strips_batch(batch, send)
             work = None
             if self.world > 1:
                 work = dist.all_to_all_single(
-                    torch.view_as_real(recv).reshape(self.world, -1),
-                    torch.view_as_real(send).reshape(self.world, -1),
+                    torch.view_as_real(recv_flat).view(self.world, -1),
+                    torch.view_as_real(send_flat).view(self.world, -1),
                     group=self.group, async_op=True)
             else:
                 recv = send

@@ -171,3 +171,90 @@ def case_fused_backward_ops_vs_oracle(make_config, W=13.5625, N=256, yB=96, yN=1
             part = part * masks[j][None, :]
         ref = oracle.add_to_facet(part, sg_off0, axis=0, out=f0[j].copy())
         pc.close(faccs[j].cpu().numpy(), ref, what=f"fold_column facet {j}")
+
+
+def case_many_sources(make_config):
+    """More facets than one launch of the fused kernel carries (64 source slots, 16 groups):
+    the C side cuts the job into several launches (api_helper.py:73-112 sums any list)."""
+    # (1) one group, 40 sources with clashing windows: 40 rounds -> pieces ADD to the output
+    cfg = make_config(13.5625, 256, 96, 128, 52, 64)
+    core = cfg.core
+    oracle = OracleCore(13.5625, 256, 64, 128)
+    rng = numpy.random.default_rng(77)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    srcs = [pc.rand_c(rng, 8, 128) for _ in range(40)]
+    offs = [int(rng.integers(-40, 40)) * Ny for _ in range(40)]
+    mask = (rng.random(52) > 0.3).astype(float)
+    out = torch.full((8, 52), 1e30 + 0j, dtype=torch.complex128, device=devof(cfg))
+    core.sum_finish_axis([(dev(cfg, s), o) for s, o in zip(srcs, offs)], out, axis=1,
+                         subgrid_off=5 * Nx, mask=dev(cfg, mask))
+    acc = None
+    for s, o in zip(srcs, offs):
+        acc = oracle.add_to_subgrid(oracle.extract_from_facet(s, 5 * Nx, axis=1), o, axis=1, out=acc)
+    ref = numpy.array([oracle.finish_subgrid(row, 5 * Nx, 52) for row in acc]) * mask[None, :]
+    pc.close(out.cpu().numpy(), ref, what="sum_finish_axis, 40 sources")
+    # (2) 20 groups in one grouped call
+    groups = [[(dev(cfg, srcs[(3 * g + k) % 40]), offs[(3 * g + k) % 40]) for k in range(3)]
+              for g in range(20)]
+    outg = torch.empty((20, 8, 52), dtype=torch.complex128, device=devof(cfg))
+    core.sum_finish_axis_grouped(groups, outg, axis=1, subgrid_off=-3 * Nx)
+    for g in range(20):
+        acc = None
+        for k in range(3):
+            i = (3 * g + k) % 40
+            acc = oracle.add_to_subgrid(oracle.extract_from_facet(srcs[i], -3 * Nx, axis=1),
+                                        offs[i], axis=1, out=acc)
+        ref = numpy.array([oracle.finish_subgrid(row, -3 * Nx, 52) for row in acc])
+        pc.close(outg[g].cpu().numpy(), ref, what=f"grouped, group {g}")
+    # (3) the advisor's reproduction: 10 x 10 facet cover through SwiftlyForward
+    W, N, yB, yN, xA, xM = 13.5625, 1024, 112, 512, 228, 256
+    cfg = make_config(W, N, yB, yN, xA, xM)
+    sources = [(1.0, 1, 0), (0.5, -300, 17), (0.25, 411, -222)]
+    facet_cfgs = make_full_facet_cover(cfg)
+    assert len(facet_cfgs) == 100
+    fwd = SwiftlyForward(cfg, [(fc, make_facet(N, fc, sources)) for fc in facet_cfgs])
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    for sg in (sg_cfgs[0], sg_cfgs[7], sg_cfgs[-1]):
+        err = check_subgrid(N, sg, fwd.get_subgrid_task(sg).tensor, sources)
+        assert err < 1e-12, err
+
+
+def case_forward_backward_vs_oracle(make_config, W=13.5625, N=2048, yB=512, yN=1024, xA=256, xM=512,
+                                    sg_variant=None):
+    """Sparse facet list, forward + backward through the fused kernels vs the oracle in the
+    reference's call order, at a geometry with xA / xM = 0.5 like the BASELINE configs: the
+    ping-pong subgrid kernel stages finished lines and hands them to the TMA engine (tensor
+    store; transposed strips)."""
+    from oracle.swiftly_oracle import backward_reference_order
+
+    cfg = make_config(W, N, yB, yN, xA, xM)
+    if sg_variant is not None:
+        import ctypes
+
+        cfg.core._lib.swiftly_b200_debug_sg_variant.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        cfg.core._lib.swiftly_b200_debug_sg_variant(cfg.core._plan, sg_variant)
+    oracle = OracleCore(W, N, xM, yN)
+    rng = numpy.random.default_rng(1)
+    offs = [(0, 0), (0, yB), (yB, 0), (-yB, 2 * yB), (2 * yB, 2 * yB)]
+    facet_cfgs = [FacetConfig(a, b, yB) for a, b in offs]
+    facets = [pc.rand_c(rng, yB, yB) for _ in offs]
+    sgs = make_full_subgrid_cover(cfg)
+    sgs = [sgs[0], sgs[1], sgs[9], sgs[-1]]
+    fwd = SwiftlyForward(cfg, list(zip(facet_cfgs, facets)), lru_forward=1, queue_size=4)
+    bwd = SwiftlyBackward(cfg, facet_cfgs, lru_backward=1, queue_size=4)
+    got = []
+    for sg in sgs:
+        task = fwd.get_subgrid_task(sg)
+        got.append(task.result())
+        bwd.add_new_subgrid_task(sg, task)
+    back = [t.result() for t in bwd.finish()]
+    sg_offs = [(s.off0, s.off1) for s in sgs]
+    ref = forward_reference_order(oracle, facets, offs, sg_offs, xA,
+                                  subgrid_masks=[(s.mask0, s.mask1) for s in sgs])
+    scale = max(numpy.abs(b).max() for b in ref)
+    for a, b in zip(got, ref):
+        assert numpy.abs(a - b).max() <= 1e-12 * scale
+    bref = backward_reference_order(oracle, ref, sg_offs, offs, yB)
+    bscale = max(numpy.abs(b).max() for b in bref)
+    for a, b in zip(back, bref):
+        assert numpy.abs(a - b).max() <= 1e-11 * bscale

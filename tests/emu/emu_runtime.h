@@ -8,6 +8,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
@@ -79,10 +80,37 @@ struct HostCtx {
     char* smem;
     EmuBlock* blk;
     inline void sync() const;
-    // named barriers: every group executes the same number of them in the kernels that use
-    // them, so a CTA-wide yield reproduces the semantics
-    inline void group_sync(int, int) const { sync(); }
+    // named barriers with the hardware's counting semantics (bar.sync / bar.arrive a, b):
+    // the barrier completes when `count` threads have arrived; bar.sync waits for that,
+    // bar.arrive does not.  A protocol error (unbalanced arrivals) shows up as a deadlock,
+    // which the scheduler detects and reports instead of hanging.
+    inline void group_sync(int id, int count) const;
+    inline void group_arrive(int id, int count) const;
+    inline void yield() const;
+    // bulk asynchronous copies: the emulated copy completes immediately (races between the
+    // asynchronous copy and ordinary accesses are NOT modelled -- only the index algebra is)
+    inline void tx_init(uint64_t* bar) const { *bar = 0; }
+    inline void tx_expect(uint64_t*, uint32_t) const {}
+    inline void tx_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) const {
+        memcpy(dst, src, bytes);
+        *bar += 1;
+    }
+    inline void tx_wait(uint64_t*, uint32_t) const {}
+    inline void bulk_prefetch_l2(const void*, uint32_t) const {}
+    inline void fence_async() const {}
+    inline void bulk_commit() const {}
+    inline void bulk_wait_read() const {}
+    inline void tensor_store(const void* map, const void* smem_src, int c1, int c2, int c3) const;
 };
+
+}  // namespace swiftly
+namespace swiftly {
+struct TensorMap4;
+void emu_tensor_store(const TensorMap4* map, const double* src, int c1, int c2, int c3);
+inline void HostCtx::tensor_store(const void* map, const void* smem_src, int c1, int c2,
+                                  int c3) const {
+    emu_tensor_store((const TensorMap4*)map, (const double*)smem_src, c1, c2, c3);
+}
 
 struct EmuBlock {
     ucontext_t main_ctx;
@@ -93,20 +121,43 @@ struct EmuBlock {
     void (*entry)(void*, HostCtx&);
     void* body;
     std::vector<HostCtx> hctx;
+    int nthreads;
+    int bar_arrived[16];
+    unsigned bar_gen[16];
+    unsigned long progress;  // barrier completions + thread exits (deadlock detection)
 };
 
 static EmuBlock* g_emu_block = nullptr;
 
-inline void HostCtx::sync() const {
+inline void HostCtx::yield() const {
     EmuBlock* b = blk;
     swapcontext(&b->ctxs[tid], &b->main_ctx);
 }
+
+inline void HostCtx::group_arrive(int id, int count) const {
+    EmuBlock* b = blk;
+    if (++b->bar_arrived[id] >= count) {
+        b->bar_arrived[id] = 0;
+        ++b->bar_gen[id];
+        ++b->progress;
+    }
+}
+
+inline void HostCtx::group_sync(int id, int count) const {
+    EmuBlock* b = blk;
+    const unsigned g = b->bar_gen[id];
+    group_arrive(id, count);
+    while (b->bar_gen[id] == g) yield();
+}
+
+inline void HostCtx::sync() const { group_sync(0, blk->nthreads); }
 
 static void emu_trampoline() {
     EmuBlock* b = g_emu_block;
     int t = b->current;
     b->entry(b->body, b->hctx[t]);
     b->done[t] = 1;
+    ++b->progress;
     // returning switches to uc_link (main_ctx)
 }
 
@@ -144,14 +195,31 @@ inline cudaError_t launch_body(const Body& body, int grid, size_t smem_bytes, cu
             blk.hctx[t].blk = &blk;
         }
         g_emu_block = &blk;
+        blk.nthreads = T;
+        for (int i = 0; i < 16; ++i) {
+            blk.bar_arrived[i] = 0;
+            blk.bar_gen[i] = 0;
+        }
+        blk.progress = 0;
         bool any = true;
+        int idle_sweeps = 0;
         while (any) {
             any = false;
+            const unsigned long before = blk.progress;
             for (int t = 0; t < T; ++t) {
                 if (blk.done[t]) continue;
                 blk.current = t;
                 swapcontext(&blk.main_ctx, &blk.ctxs[t]);
                 if (!blk.done[t]) any = true;
+            }
+            // a sweep lets every live thread run to its next wait; two sweeps in a row without
+            // a barrier completing or a thread finishing means nobody can ever proceed
+            idle_sweeps = (any && blk.progress == before) ? idle_sweeps + 1 : 0;
+            if (idle_sweeps >= 2) {
+                fprintf(stderr, "swiftly emulator: barrier DEADLOCK in block %d (arrivals:", bid);
+                for (int i = 0; i < 16; ++i) fprintf(stderr, " %d", blk.bar_arrived[i]);
+                fprintf(stderr, ")\n");
+                abort();
             }
         }
     }

@@ -40,3 +40,14 @@ def test_emu_fused_backward_ops_vs_oracle():
     api_cases.case_fused_backward_ops_vs_oracle(make_config, force_split=True)
     api_cases.case_fused_backward_ops_vs_oracle(make_config, W=11.0, N=1280, yB=440, yN=640,
                                                 xA=280, xM=320)
+
+
+def test_emu_many_sources():
+    api_cases.case_many_sources(make_config)
+
+
+@pytest.mark.parametrize("sg_variant", [0, 1, 2, 5])
+def test_emu_forward_backward_vs_oracle_kernel_variants(sg_variant):
+    """Every variant of the fused subgrid kernel (0: ping-pong + tokens + TMA tensor stores,
+    1: round-1 kernel, 2: ping-pong without tokens, 5: ping-pong with direct stores)."""
+    api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)

@@ -43,6 +43,17 @@ def test_fused_backward_ops_vs_oracle():
                                                 xM=2048)
 
 
+@pytest.mark.parametrize("sg_variant", [0, 1, 2, 5])
+def test_forward_backward_vs_oracle_kernel_variants(sg_variant):
+    """Every variant of the fused subgrid kernel against the oracle (N=2048, xA/xM = 0.5)."""
+    api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)
+
+
+def test_many_sources():
+    """More sources / groups than one fused launch carries (10 x 10 facets and beyond)."""
+    api_cases.case_many_sources(make_config)
+
+
 def test_forward_backward_vs_reference_golden(golden_2d):
     api_cases.case_forward_backward_vs_reference_golden(make_config, golden_2d)
 
@@ -83,6 +94,90 @@ def test_cfg2_forward_vs_oracle_and_dft():
     for sg in (sg_cfgs[0], sg_cfgs[9], sg_cfgs[-1]):
         err = check_subgrid(N, sg, fwd.get_subgrid_task(sg).tensor, sources)
         assert err < 1e-13, err
+
+
+def test_cfg3_forward_vs_oracle():
+    """BASELINE cfg3 (N=32768, yN=8192: K2 as the direct 8192-point line kernel, m=1024,
+    xM=4096) in 2-D: two dense facets x three subgrids through SwiftlyForward vs the oracle in
+    the reference's call order, and point sources vs the analytic DFT."""
+    W, N, yB, yN, xA, xM = 13.5625, 32768, 4096, 8192, 2048, 4096
+    cfg = make_config(W, N, yB, yN, xA, xM)
+    oracle = OracleCore(W, N, xM, yN)
+    rng = numpy.random.default_rng(32768)
+    offs = [(0, 4096), (-8192, 4096 * 5)]
+    facets = [pc.rand_c(rng, yB, yB) for _ in offs]
+    sgs = [SubgridConfig(2048, 6144, xA), SubgridConfig(2048, 0, xA),
+           SubgridConfig(-4096, 2048 * 7, xA)]
+    fwd = SwiftlyForward(cfg, [(FacetConfig(o0, o1, yB), f) for (o0, o1), f in zip(offs, facets)])
+    got = [fwd.get_subgrid_task(sg).result() for sg in sgs]
+    del fwd
+    ref = forward_reference_order(oracle, facets, offs, [(s.off0, s.off1) for s in sgs], xA)
+    for a, b in zip(got, ref):
+        assert numpy.abs(a - b).max() <= 1e-11 * numpy.abs(b).max()
+    del facets, ref, got
+    torch.cuda.empty_cache()
+    fcs = [FacetConfig(4096, 0, yB), FacetConfig(4096 * 3, 4096 * 6, yB)]
+    sources = []
+    for fc in fcs:
+        for _ in range(5):
+            l = (fc.off0 + int(rng.integers(-yB // 2, yB // 2)) + N // 2) % N - N // 2
+            m_ = (fc.off1 + int(rng.integers(-yB // 2, yB // 2)) + N // 2) % N - N // 2
+            sources.append((float(rng.random()) + 0.5, l, m_))
+    fwd = SwiftlyForward(cfg, [(fc, make_facet(N, fc, sources)) for fc in fcs])
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    scale = sum(s[0] for s in sources) / N**2
+    for sg in (sg_cfgs[0], sg_cfgs[100], sg_cfgs[-1]):
+        err = check_subgrid(N, sg, fwd.get_subgrid_task(sg).tensor, sources)
+        assert err / scale < 1e-9, (err, scale)
+
+
+def _sources_inside(rng, fcs, N, yB, per_facet):
+    sources = []
+    for fc in fcs:
+        for _ in range(per_facet):
+            l = (fc.off0 + int(rng.integers(-yB // 2, yB // 2)) + N // 2) % N - N // 2
+            m_ = (fc.off1 + int(rng.integers(-yB // 2, yB // 2)) + N // 2) % N - N // 2
+            sources.append((float(rng.random()) + 0.5, l, m_))
+    return sources
+
+
+def test_cfg5_sparse_facets_full_size():
+    """BASELINE cfg5: the cfg4 geometry (N=65536) with 25 % of the facets -- the central 4 x 4
+    block, offsets {0, 8192, 49152, 57344}^2 -- and the 7-facet disc cover the
+    reference's demo builds (scripts/demo_sparse_facet.py:106-134).  Point sources inside the
+    covered facets: every subgrid must equal the analytic DFT."""
+    import os
+    import sys
+
+    W, N, yB, yN, xA, xM = 13.5625, 65536, 8192, 16384, 2048, 4096
+    cfg = make_config(W, N, yB, yN, xA, xM)
+    rng = numpy.random.default_rng(5)
+    block = [0, 8192, 49152, 57344]
+    fcs = [FacetConfig(a, b, yB) for a in block for b in block]
+    sources = _sources_inside(rng, fcs[::3], N, yB, 2)
+    scale = sum(s[0] for s in sources) / N**2
+    # facets are built on demand (one 1 GiB host array at a time)
+    fwd = SwiftlyForward(cfg, [(fc, (lambda fc=fc: make_facet(N, fc, sources))) for fc in fcs])
+    sg_cfgs = make_full_subgrid_cover(cfg)
+    for sg in (sg_cfgs[0], sg_cfgs[517], sg_cfgs[-1]):
+        err = check_subgrid(N, sg, fwd.get_subgrid_task(sg).tensor, sources)
+        assert err / scale < 1e-9, (err, scale)
+    del fwd
+    torch.cuda.empty_cache()
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "scripts"))
+    from demo_sparse_facet import disc_cover_offsets  # pylint: disable=import-error
+
+    offsets = disc_cover_offsets(N, yB, 2.12 * yB)
+    assert len(offsets) == 7
+    assert all(o0 % cfg.facet_off_step == 0 and o1 % cfg.facet_off_step == 0 for o0, o1 in offsets)
+    fcs = [FacetConfig(o0, o1, yB) for o0, o1 in offsets]
+    sources = _sources_inside(rng, fcs[:3], N, yB, 2)
+    scale = sum(s[0] for s in sources) / N**2
+    fwd = SwiftlyForward(cfg, [(fc, (lambda fc=fc: make_facet(N, fc, sources))) for fc in fcs])
+    for sg in (sg_cfgs[31], sg_cfgs[600]):
+        err = check_subgrid(N, sg, fwd.get_subgrid_task(sg).tensor, sources)
+        assert err / scale < 1e-9, (err, scale)
 
 
 def test_catalogue_config_round_trip():

@@ -45,11 +45,38 @@ by = 16 * (m * yB + m * yN)
 print(f"F2 extract_column:   {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
 for i in range(1, nf):
     core.extract_column(bf, 4096, 8192 * i, out=nmbf[i])
+import ctypes  # noqa: E402
+
+core._lib.swiftly_b200_debug_sg_variant.argtypes = [ctypes.c_void_p, ctypes.c_int]
+bfs = [bf] * nf
+offs = [yB * i for i in range(nf)]
+by = 16 * (m * yB + m * yN) * nf
+keep = None
+for variant, name in ((4, "round-1 kernel"), (0, "TMA-staged rows")):
+    core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
+    t, ta = timeit(lambda: core.extract_columns(bfs, 4096, offs, outs=nmbf))
+    print(f"F2 extract_columns x{nf} [{name}]: {t:.3f} ms (avg {ta:.3f})  frac {by/t*1e3/HBM:.3f}")
+    if keep is None:
+        keep = nmbf[3].clone()
+    else:
+        print(f"   max |diff|: {(nmbf[3] - keep).abs().max().item():.3e} (max |ref| {keep.abs().max().item():.3e})")
+core._lib.swiftly_b200_debug_sg_variant(core._plan, 0)
 strips = torch.empty(nf, m, xA, dtype=torch.complex128, device=dev)
 srcs = [(nmbf[i], i * yB) for i in range(nf)]
-t, ta = timeit(lambda: core.sum_finish_axis(srcs, strips[0], axis=1, subgrid_off=2048))
-by = 16 * (nf * m * m + m * xA)
-print(f"F3 sum_finish ax1 ({nf} src): {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
+ref = None
+for variant, name in ((1, "round-1 kernel"), (2, "ping-pong layout, no tokens"), (0, "ping-pong + tokens")):
+    core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
+    t, ta = timeit(lambda: core.sum_finish_axis(srcs, strips[0], axis=1, subgrid_off=2048))
+    by = 16 * (nf * m * m + m * xA)
+    print(f"F3 sum_finish ax1 ({nf} src) [{name}]: {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
+    # as the step launches it: all 8 facet rows of a subgrid in one grouped launch
+    t, ta = timeit(lambda: core.sum_finish_axis_grouped([srcs] * nf, strips, axis=1, subgrid_off=2048))
+    by = 16 * nf * (nf * m * m + m * xA)
+    print(f"F3 grouped x{nf} [{name}]: {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
+    if ref is None:
+        ref = strips.clone()
+    else:
+        print(f"   max |diff| vs round-1 kernel: {(strips - ref).abs().max().item():.3e} (max |ref| {ref.abs().max().item():.3e})")
 for i in range(1, nf):
     core.sum_finish_axis(srcs, strips[i], axis=1, subgrid_off=2048)
 out = torch.empty(xA, xA, dtype=torch.complex128, device=dev)
@@ -57,6 +84,22 @@ srcs0 = [(strips[i], i * yB) for i in range(nf)]
 t, ta = timeit(lambda: core.sum_finish_axis(srcs0, out, axis=0, subgrid_off=4096))
 by = 16 * (nf * m * xA + xA * xA)
 print(f"F4 sum_finish ax0 ({nf} src): {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
+# transposed strips (what the product uses): finished lines leave through the TMA engine
+ref0 = out.clone()
+strips_t = torch.empty(nf, xA, m, dtype=torch.complex128, device=dev).transpose(1, 2)
+for variant, name in ((5, "ping-pong + tokens, direct 16-byte stores"), (2, "ping-pong, no tokens, TMA tensor stores"),
+                      (0, "ping-pong + tokens, TMA tensor stores")):
+    core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
+    t, ta = timeit(lambda: core.sum_finish_axis_grouped([srcs] * nf, strips_t, axis=1, subgrid_off=2048))
+    by = 16 * nf * (nf * m * m + m * xA)
+    print(f"F3 grouped x{nf} -> TRANSPOSED strips [{name}]: {t:.3f} ms (avg {ta:.3f})  frac {by/t*1e3/HBM:.3f}")
+    print(f"   max |diff| vs row-major strips: {(strips_t - ref).abs().max().item():.3e}")
+    srcs0t = [(strips_t[i], i * yB) for i in range(nf)]
+    t, ta = timeit(lambda: core.sum_finish_axis(srcs0t, out, axis=0, subgrid_off=4096))
+    by = 16 * (nf * m * xA + xA * xA)
+    print(f"F4 sum_finish ax0 from TRANSPOSED strips [{name}]: {t:.3f} ms (avg {ta:.3f})  frac {by/t*1e3/HBM:.3f}")
+    print(f"   max |diff| vs row-major path: {(out - ref0).abs().max().item():.3e} (max |ref| {ref0.abs().max().item():.3e})")
+core._lib.swiftly_b200_debug_sg_variant(core._plan, 0)
 # plain copy for reference
 a = torch.empty(1 << 27, dtype=torch.complex128, device=dev)
 b = torch.empty_like(a)
