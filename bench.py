@@ -39,7 +39,10 @@ WORKLOADS = {
     "cfg2": "8k[1]-n4k-2k",
     "cfg3": "32k[1]-n8k-4k",
     "cfg4": "64k[1]-n16k-4k",
+    # BASELINE "sparse-facet" config: cfg4 geometry, 25 % of the facets (central 4 x 4 block)
+    "cfg5": "64k[1]-n16k-4k",
 }
+SPARSE_BLOCKS = {"cfg5": [0, 8192, 49152, 57344]}
 METRIC = "facet->subgrid contributions/sec"
 UNIT = "contributions/s"
 
@@ -164,113 +167,30 @@ class ClockSampler:
         return out
 
 
-# ====================================================================== CPU arm (oracle)
-def _cpu_stage_sample(args):
-    """Time the per-stage unit costs of the reference algorithm (oracle port) once.
-
-    Runs in a worker process; returns per-unit seconds for the stage model of
-    ``cpu_model_rate``.  Stage 1 is timed on a slab of ``cols1`` facet columns (lines are
-    independent) and scaled to the full facet.
-    """
-    params, cols1, seed = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    from oracle.swiftly_oracle import OracleCore
-
-    p = params
-    core = _cpu_stage_sample.cache.get("core")
-    if core is None:
-        core = OracleCore(p["W"], p["N"], p["xM_size"], p["yN_size"])
-        _cpu_stage_sample.cache["core"] = core
-    yB, yN, xA, xM, m = p["yB_size"], p["yN_size"], p["xA_size"], p["xM_size"], core.xM_yN_size
-    rng = numpy.random.default_rng(seed)
-    Nx, Ny = core.subgrid_off_step, core.facet_off_step
-
-    def rc(*s):
-        return rng.standard_normal(s) + 1j * rng.standard_normal(s)
-
-    t = {}
-    slab = rc(yB, cols1)
-    t0 = time.perf_counter()
-    bf = core.prepare_facet(slab, 3 * Ny, axis=0)
-    t["stage1_prepare_facet_ax0"] = (time.perf_counter() - t0) * (yB / cols1)
-    bf_full = rc(yN, min(yB, 4 * cols1))  # stands for BF_F; width scales stage 2a / 2b
-    scale2 = yB / bf_full.shape[1]
-    t0 = time.perf_counter()
-    rows = core.extract_from_facet(bf_full, 5 * Nx, axis=0)
-    t["stage2a_extract_ax0"] = (time.perf_counter() - t0) * scale2
-    rows_full = rc(m, yB)
-    t0 = time.perf_counter()
-    nmbf = core.prepare_facet(rows_full, -2 * Ny, axis=1)
-    t["stage2b_prepare_facet_ax1"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    contrib = core.extract_from_facet(nmbf, 7 * Nx, axis=1)
-    t["stage3_extract_ax1"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    col = core.add_to_subgrid(contrib, 3 * Ny, axis=0)
-    t["stage4_add_to_subgrid_ax0"] = time.perf_counter() - t0
-    acc = numpy.zeros((xM, xM), dtype=complex)
-    t0 = time.perf_counter()
-    acc = core.add_to_subgrid(col, -2 * Ny, axis=1, out=acc)
-    t["stage5_add_to_subgrid_ax1"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    core.finish_subgrid(acc, [5 * Nx, 7 * Nx], xA)
-    t["stage6_finish_subgrid"] = time.perf_counter() - t0
-    del bf, rows
-    return t
+# ====================================================================== CPU arm
+def cpu_facets_per_step(params, cores):
+    """Facets of the column slice one CPU step runs (bounds a step to a few seconds)."""
+    N, yB = params["N"], params["yB_size"]
+    F = (-(-N // yB)) ** 2
+    return max(1, min(F, cores))
 
 
-_cpu_stage_sample.cache = {}
+def cpu_baseline_entry(params, cores, steps=1, warmup=0):
+    """The reference algorithm RUNNING on the host cores (oracle/cpu_arm.py): one timed
+    subgrid column of the forward transform per step -- real shapes, reference task order,
+    all cores -- no unit-cost model."""
+    from oracle.cpu_arm import run_column_slice
 
-
-def cpu_model_rate(params, unit_times, cores):
-    """contributions/s of the reference task graph on ``cores`` independent workers.
-
-    T_full = F t1 + ns F (t2a + t2b) + S F (t3 + t4) + S nf1 t5 + S t6   (SURVEY.md 3.2),
-    every task single threaded (numpy FFT), tasks embarrassingly parallel across workers
-    like the reference's Dask graph; unit times measured with all workers busy.
-    """
-    N, yB, xA = params["N"], params["yB_size"], params["xA_size"]
-    nf1 = -(-N // yB)
-    F = nf1 * nf1
-    ns = -(-N // xA)
-    S = ns * ns
-    u = unit_times
-    total = (F * u["stage1_prepare_facet_ax0"]
-             + ns * F * (u["stage2a_extract_ax0"] + u["stage2b_prepare_facet_ax1"])
-             + S * F * (u["stage3_extract_ax1"] + u["stage4_add_to_subgrid_ax0"])
-             + S * nf1 * u["stage5_add_to_subgrid_ax1"]
-             + S * u["stage6_finish_subgrid"])
-    return F * S / (total / cores), total
-
-
-def run_cpu_sample(params, cores, repeats=1, cols1=None):
-    """Run the stage sample on ``cores`` worker processes simultaneously."""
-    import multiprocessing as mp
-
-    if cols1 is None:
-        cols1 = max(16, min(params["yB_size"], (1 << 22) // params["yN_size"]))
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        results = []
-        for rep in range(repeats):
-            results += pool.map(_cpu_stage_sample, [(params, cols1, 1000 * rep + i) for i in range(cores)])
-    wall = time.perf_counter() - t0
-    keys = results[0].keys()
-    unit = {k: float(numpy.mean([r[k] for r in results])) for k in keys}
-    return unit, wall, cols1
-
-
-def cpu_baseline_entry(params, cores, repeats=1):
-    unit, wall, cols1 = run_cpu_sample(params, cores, repeats)
-    rate, total = cpu_model_rate(params, unit, cores)
-    sample = (f"oracle (numpy port of the reference SwiftlyCore + task order) on {cores} worker "
-              f"processes, each timing every stage unit once per repeat (stage 1 on a {cols1}-column "
-              f"slab scaled to the facet); rate from the reference task-count model; "
-              f"sample wall {wall:.1f} s")
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "model_full_transform_core_seconds": total, "stage_unit_seconds": unit}
+    nf = cpu_facets_per_step(params, cores)
+    for _ in range(warmup):
+        run_column_slice(params, cores, max_facets=nf)
+    runs = [run_column_slice(params, cores, max_facets=nf) for _ in range(max(1, steps))]
+    rate = float(numpy.mean([r["rate"] for r in runs]))
+    last = runs[-1]
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": last["kind"],
+            "sample": last["sample"], "steps": len(runs),
+            "step_wall_s": [r["wall_s"] for r in runs],
+            "phase_a_s": last["phase_a_s"], "phase_b_s": last["phase_b_s"]}
 
 
 def main_reference(args):
@@ -279,15 +199,13 @@ def main_reference(args):
         return
     params = workload_params(args.workload)
     cores = args.cpu_cores or host_cores()
-    for _ in range(max(0, min(args.warmup, 1))):
-        run_cpu_sample(params, cores, 1)
-    t0 = time.perf_counter()
-    entry = cpu_baseline_entry(params, cores, repeats=max(1, args.steps))
-    wall = time.perf_counter() - t0
+    entry = cpu_baseline_entry(params, cores, steps=max(1, args.steps),
+                               warmup=max(0, min(args.warmup, 1)))
     line = {
         "impl": "reference", "metric": METRIC, "value": entry["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
+        "ms_per_step": 1e3 * float(numpy.mean(entry["step_wall_s"])),
+        "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)",
         "data": "synthetic", "config": workload_config(args.workload, params, args.gpus),
         "cpu_baseline": entry,
@@ -297,15 +215,27 @@ def main_reference(args):
     print(json.dumps(line))
 
 
+def workload_facet_offsets(name):
+    """Facet mid-point offsets of a sparse workload (None: full cover)."""
+    block = SPARSE_BLOCKS.get(name)
+    if block is None:
+        return None
+    return [(a, b) for a in block for b in block]
+
+
 def workload_config(name, params, gpus):
     N, yB, xA = params["N"], params["yB_size"], params["xA_size"]
     nf = -(-N // yB)
     ns = -(-N // xA)
+    sparse = workload_facet_offsets(name)
+    n_facets = nf * nf if sparse is None else len(sparse)
+    facets = (f"{nf}x{nf} facets" if sparse is None else
+              f"{n_facets} of {nf * nf} facets (central block, offsets {SPARSE_BLOCKS[name]}^2)")
     return {
-        "workload": f"{name}: 2D N={N}, {nf}x{nf} facets of {yB}^2 -> {ns}x{ns} subgrids of "
+        "workload": f"{name}: 2D N={N}, {facets} of {yB}^2 -> {ns}x{ns} subgrids of "
                     f"{xA}^2, yN={params['yN_size']}, xM={params['xM_size']}, W={params['W']}, "
                     f"complex128, dense standard-normal facets",
-        "contributions_per_step": nf * nf * ns * ns,
+        "contributions_per_step": n_facets * ns * ns,
         "parallelism": "1 GPU" if gpus == 1 else f"facet rows sharded over {gpus} GPUs, "
                        "strips exchanged per subgrid batch",
         "l2": "inputs (>= 64 GiB/step) far larger than the 126 MB L2; no flush needed",
@@ -331,6 +261,61 @@ def main_gpu(args):
         sys.stdout.flush()
 
 
+def _main_gpu_backward(args, dev, rank, world):
+    """``--direction backward``: the subgrid -> facet transform (reference api.py:327-463),
+    same JSON schema; metric = (#facets x #subgrids) / step time."""
+    import torch
+
+    from ska_sdp_distributed_fourier_transform_b200 import bench_support as bs
+
+    params = workload_params(args.workload)
+    note(f"setting up backward {args.workload} on {world} GPU(s)")
+    runner = bs.BackwardBenchRunner(params, dev, rank, world)
+    hbm_gbs, peak_src = measured_peaks()
+    for i in range(args.warmup):
+        runner.step(timed=False)
+        note(f"warm-up step {i + 1}/{args.warmup} done")
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    times = []
+    for i in range(args.steps):
+        times.append(runner.step(timed=True))
+        note(f"timed step {i + 1}/{args.steps}: {times[-1]:.1f} ms "
+             f"(subgrids {runner.last_parts[0]:.1f} + finish {runner.last_parts[1]:.1f})")
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(numpy.mean(times))
+    parity = None if args.no_selfcheck else runner.selfcheck()
+    extra = runner.kernel_rooflines(hbm_gbs) if not args.no_roofline else None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    cfgd = workload_config(args.workload, params, world)
+    cfgd["direction"] = "backward (subgrid -> facet): SwiftlyBackward.add_new_subgrid_task for " \
+                        "every subgrid of the cover + finish()"
+    cfgd["inputs"] = "32 distinct random subgrids fed cyclically (values do not affect timing)"
+    line = {
+        "metric": "subgrid->facet contributions/sec", "value": runner.contributions_per_step / (ms * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 (complex128)", "data": "synthetic", "config": cfgd, "step_ms": times,
+        "clocks": clocks, "direction": "backward",
+        "max_memory_gib": torch.cuda.max_memory_allocated(dev) / 2**30,
+    }
+    if parity is not None:
+        line["parity_max_rel_err"] = parity["parity_max_rel_err"]
+        line["parity_check"] = parity
+    if extra:
+        line["roofline"] = extra["dominant"]
+        line["roofline"]["peak_source"] = peak_src
+        line["kernel_rooflines"] = extra["kernels"]
+    return line
+
+
 def _main_gpu(args):
     import torch
 
@@ -349,11 +334,14 @@ def _main_gpu(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
+    if args.direction == "backward":
+        return _main_gpu_backward(args, dev, rank, world)
     from ska_sdp_distributed_fourier_transform_b200 import bench_support as bs
 
     params = workload_params(args.workload)
     note(f"setting up {args.workload} on {world} GPU(s)")
-    runner = bs.ForwardBenchRunner(params, dev, rank, world, exchange=args.exchange)
+    runner = bs.ForwardBenchRunner(params, dev, rank, world, exchange=args.exchange,
+                                   facet_offsets=workload_facet_offsets(args.workload))
     hbm_gbs, peak_src = measured_peaks()
 
     # ---- device-resident runs (value) ----------------------------------------------
@@ -387,7 +375,7 @@ def _main_gpu(args):
         note(f"e2e done: {e2e['ms_per_step']:.1f} ms/step")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_entry(params, args.cpu_cores or host_cores())
+        cpu = cpu_baseline_entry(params, args.cpu_cores or host_cores(), steps=1)
         note("cpu baseline done")
     if world > 1:
         import torch.distributed as dist
@@ -430,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--direction", default="forward", choices=["forward", "backward"],
+                    help="forward = facet -> subgrid (the headline metric); backward = subgrid -> facet")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")

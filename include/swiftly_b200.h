@@ -149,13 +149,36 @@ int swiftly_b200_sum_finish_axis_grouped(const swiftly_b200* plan,
                                          const swiftly_b200_lines* out, int64_t out_group_stride,
                                          int64_t subgrid_off, const double* mask, void* stream);
 /* As above, but the groups may belong to different subgrids (a batch of the multi-GPU
- * driver): subgrid_offs[g] and masks[g] (masks or masks[g] may be NULL) per group; <= 16 groups. */
+ * driver): subgrid_offs[g] and masks[g] (masks or masks[g] may be NULL) per group
+ * (any number of groups: larger jobs are cut into several launches). */
 int swiftly_b200_sum_finish_axis_batched(const swiftly_b200* plan,
                                          const swiftly_b200_source* sources,
                                          const int32_t* group_sizes, int n_groups,
                                          const swiftly_b200_lines* out, int64_t out_group_stride,
                                          const int64_t* subgrid_offs, const double* const* masks,
                                          void* stream);
+/* As swiftly_b200_sum_finish_axis_batched, but every group writes to its OWN buffer:
+ * out_ptrs[g] is the base address of group g's output, `out` gives the (common) shape and
+ * strides.  The sharded driver passes the owners' peer-mapped receive buffers, so the strips
+ * of a subgrid travel over NVLink as the kernel's epilogue (TMA bulk tensor stores) instead
+ * of through a separate collective (replaces the Dask transfer of contributions,
+ * reference api.py:263-277). */
+int swiftly_b200_sum_finish_axis_scattered(const swiftly_b200* plan,
+                                           const swiftly_b200_source* sources,
+                                           const int32_t* group_sizes, int n_groups,
+                                           const swiftly_b200_lines* out, void* const* out_ptrs,
+                                           const int64_t* subgrid_offs,
+                                           const double* const* masks, void* stream);
+/* Ordering between the ranks of the sharded transform (peer_sync.cu): `flags_dev_table` is a
+ * DEVICE array of n_peers device pointers -- this rank's mappings of every rank's flag array
+ * (n_peers int64 each, peer-mapped / symmetric memory).  signal stores `value` into entry
+ * my_rank of every rank's array (system-scope release, after everything queued before on the
+ * stream); wait spins (system-scope acquire) until all n_peers entries of `my_flags` are
+ * >= value, or sets *status (device int) to 1 + peer after timeout_s. */
+int swiftly_b200_peer_signal(const swiftly_b200* plan, void* const* flags_dev_table, int n_peers,
+                             int my_rank, int64_t value, void* stream);
+int swiftly_b200_peer_wait(const swiftly_b200* plan, const void* my_flags, int n_peers,
+                           int64_t value, double timeout_s, void* status, void* stream);
 /* swiftly_b200_extract_column for n_facets (<= 64) facets in ONE launch: bf_f[f] / out[f]
  * as in swiftly_b200_extract_column (contiguous rows), facet_off1[f] per facet. */
 int swiftly_b200_extract_columns(const swiftly_b200* plan, int n_facets,

@@ -75,6 +75,9 @@ SYMBOLS = {
     "swiftly_b200_sum_finish_axis": (ctypes.c_int, [_PLAN, ctypes.POINTER(Source), ctypes.c_int, _LINES_P, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "swiftly_b200_sum_finish_axis_grouped": (ctypes.c_int, [_PLAN, ctypes.POINTER(Source), ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _LINES_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "swiftly_b200_sum_finish_axis_batched": (ctypes.c_int, [_PLAN, ctypes.POINTER(Source), ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _LINES_P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "swiftly_b200_sum_finish_axis_scattered": (ctypes.c_int, [_PLAN, ctypes.POINTER(Source), ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _LINES_P, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "swiftly_b200_peer_signal": (ctypes.c_int, [_PLAN, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p]),
+    "swiftly_b200_peer_wait": (ctypes.c_int, [_PLAN, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "swiftly_b200_extract_columns": (ctypes.c_int, [_PLAN, ctypes.c_int, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]),
     "swiftly_b200_subgrid_to_facets": (ctypes.c_int, [_PLAN, ctypes.c_int, _LINES_P, _LINES_P, ctypes.POINTER(ctypes.c_int64), ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_fold_column": (ctypes.c_int, [_PLAN, ctypes.c_int, _LINES_P, _LINES_P, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64, ctypes.c_void_p]),

@@ -508,9 +508,21 @@ class SwiftlyBackward:
                 blocks[cfg.off0] = core.extract_from_subgrid(prepared, cfg.off0, axis=0)
         column = self.lru.get(off0)
         if column is None:
-            shape = (core.xM_yN_size, core.yN_size)
-            column = [torch.zeros(shape, dtype=torch.complex128, device=self.device)
-                      for _ in self.facets_config_list]
+            reuse = None
+            if len(self.lru.data) >= self.lru.size:
+                # fold the column that is about to be evicted NOW and recycle its buffers:
+                # allocating the new column first would hold two columns (2 x 16 GiB at
+                # N=65536) next to the 128 GiB of facet accumulators
+                old_off0, reuse = self.lru.data.popitem(last=False)
+                self.update_MNAF_BMNAFs(old_off0, reuse)
+            if reuse is not None:
+                column = reuse
+                for acc in column:
+                    acc.zero_()
+            else:
+                shape = (core.xM_yN_size, core.yN_size)
+                column = [torch.zeros(shape, dtype=torch.complex128, device=self.device)
+                          for _ in self.facets_config_list]
         core.subgrid_to_facets(
             [blocks[cfg.off0] for cfg in self.facets_config_list], column,
             [cfg.off1 for cfg in self.facets_config_list], off1)

@@ -13,13 +13,15 @@ import torch
 import torch.distributed as dist
 
 from .api import (
+    FacetConfig,
+    SwiftlyBackward,
     SwiftlyConfig,
     SwiftlyForward,
     make_full_facet_cover,
     make_full_subgrid_cover,
 )
 from .api_helper import make_facet_device
-from .distributed import SwiftlyForwardSharded, partition_facets
+from .distributed import SwiftlyBackwardSharded, SwiftlyForwardSharded, partition_facets
 from .fourier_algorithm import make_subgrid_from_sources
 
 MIB = float(1 << 20)
@@ -29,7 +31,7 @@ class ForwardBenchRunner:
     """Synthetic full-cover forward transform of one parameter set on ``world`` GPUs."""
 
     # pylint: disable=too-many-instance-attributes
-    def __init__(self, params, device, rank=0, world=1, exchange="auto"):
+    def __init__(self, params, device, rank=0, world=1, exchange="auto", facet_offsets=None):
         self.exchange = exchange
         self.exchange_used = None
         self.params = dict(params)
@@ -39,6 +41,9 @@ class ForwardBenchRunner:
         self.cfg = SwiftlyConfig(device=device.index, **params)
         self.core = self.cfg.core
         self.facet_cfgs = make_full_facet_cover(self.cfg)
+        self.sparse = facet_offsets is not None
+        if facet_offsets is not None:  # sparse cover: facets at the given mid-point offsets
+            self.facet_cfgs = [FacetConfig(a, b, params["yB_size"]) for a, b in facet_offsets]
         self.sg_cfgs = make_full_subgrid_cover(self.cfg)
         self.owner = partition_facets(self.facet_cfgs, world)
         self.local_idx = [i for i, o in enumerate(self.owner) if o == rank]
@@ -98,6 +103,9 @@ class ForwardBenchRunner:
                                     bf_f_buffers=self.bf_views, exchange=self.exchange)
         self.exchange_used = fwd.exchange
         fwd.get_subgrid_tasks(self.sg_cfgs, consumer=consumer or (lambda *a: None))
+        # our kernels actually launched by this rank in the step (+ signal / wait per batch)
+        nb = -(-len(self.sg_cfgs) // self.world)
+        self.launches_per_step = fwd.launches + (2 * nb if fwd.exchange == "p2p" else 0)
 
     def _barrier(self):
         torch.cuda.synchronize(self.device)
@@ -134,8 +142,17 @@ class ForwardBenchRunner:
         """
         N = self.params["N"]
         rng = numpy.random.default_rng(20260922)  # same sources on every rank
-        sources = [(float(rng.random()) + 0.5, int(rng.integers(-N // 2, N // 2)),
-                    int(rng.integers(-N // 2, N // 2))) for _ in range(n_sources)]
+        if self.sparse:
+            # sparse cover: the sources must lie inside covered facets
+            sources = []
+            for _ in range(n_sources):
+                fc = self.facet_cfgs[int(rng.integers(len(self.facet_cfgs)))]
+                pos = [(off + int(rng.integers(-self.yB // 2, self.yB // 2)) + N // 2) % N - N // 2
+                       for off in (fc.off0, fc.off1)]
+                sources.append((float(rng.random()) + 0.5, pos[0], pos[1]))
+        else:
+            sources = [(float(rng.random()) + 0.5, int(rng.integers(-N // 2, N // 2)),
+                        int(rng.integers(-N // 2, N // 2))) for _ in range(n_sources)]
         for idx in self.local_idx:
             make_facet_device(N, self.facet_cfgs[idx], sources, self.device,
                               out=self.facet_views[idx])
@@ -221,12 +238,27 @@ class ForwardBenchRunner:
         local_rows = sorted({fcs[i].off0 for i in self.local_idx})
         groups = [[(nmbf[i], fcs[i].off1) for i in self.local_idx if fcs[i].off0 == o]
                   for o in local_rows]
-        t3 = self._time(lambda: core.sum_finish_axis_grouped(
-            groups, strips[:len(groups)], axis=1, subgrid_off=sg.off1))
-        out["sum_finish_axis1 (all local facet rows of a subgrid)"] = (
-            t3, 16.0 * (F * m * m + len(groups) * m * xA), S)
+        # strips are stored transposed (contribution index contiguous), as in the step
+        strips = torch.empty((nstrips, xA, m), dtype=torch.complex128, device=dev).transpose(1, 2)
+        if self.world == 1:
+            t3 = self._time(lambda: core.sum_finish_axis_grouped(
+                groups, strips[:len(groups)], axis=1, subgrid_off=sg.off1))
+            out["sum_finish_axis1 (all local facet rows of a subgrid)"] = (
+                t3, 16.0 * (F * m * m + len(groups) * m * xA), S)
+        else:
+            # the step launches the axis-1 kernel for a whole batch: world subgrids of one
+            # subgrid column x local facet rows, every group with its own subgrid offset
+            batch = [s_ for s_ in self.sg_cfgs if s_.off0 == sg.off0][:self.world]
+            bgroups = [g for _ in batch for g in groups]
+            boffs = [s_.off1 for s_ in batch for _ in groups]
+            bout = torch.empty((len(bgroups), xA, m), dtype=torch.complex128,
+                               device=dev).transpose(1, 2)
+            t3 = self._time(lambda: core.sum_finish_axis_grouped(
+                bgroups, bout, axis=1, subgrid_off=boffs, mask=None))
+            out[f"sum_finish_axis1 (batch of {len(batch)} subgrids x local facet rows)"] = (
+                t3, 16.0 * len(batch) * (F * m * m + len(groups) * m * xA), -(-S // self.world))
         srcs = groups[0]
-        for r in range(len(groups), nstrips):
+        for r in range(nstrips):
             core.sum_finish_axis(srcs, strips[r], axis=1, subgrid_off=sg.off1)
         res = torch.empty((xA, xA), dtype=torch.complex128, device=dev)
         row_offs = sorted({c.off0 for c in fcs})
@@ -249,9 +281,13 @@ class ForwardBenchRunner:
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
         bmin = None
         if step_ms:
-            by = 32.0 * MIB * self.contributions_per_step / self.world
+            # B_min of SURVEY.md section 8d, evaluated for this cover
+            F_all, S_all = len(fcs), len(self.sg_cfgs)
+            per = 16.0 * (F_all * (yB * yB + yN * yB) + ncols * F_all * (m * yB + m * yN)
+                          + S_all * F_all * m * m + S_all * xA * xA) / (S_all * F_all)
+            by = per * self.contributions_per_step / self.world
             ach = by / (step_ms * 1e-3) / 1e9
-            bmin = {"bytes_per_contribution": 32.0 * MIB, "achieved": ach, "unit": "GB/s",
+            bmin = {"bytes_per_contribution": per, "achieved": ach, "unit": "GB/s",
                     "frac": ach / hbm_gbs, "note": "end-to-end B_min of SURVEY.md section 8d per GPU"}
         return {"kernels": kernels, "dominant": dominant, "bmin": bmin}
 
@@ -314,3 +350,206 @@ class ForwardBenchRunner:
             "path": "SwiftlyForward(host pinned facets) -> get_subgrid_task -> pinned host "
                     "subgrids; wall clock between device synchronisations, max over ranks",
         }
+
+
+class BackwardBenchRunner:
+    """Synthetic full-cover BACKWARD transform (subgrid -> facet, reference ``api.py:327-463``)
+    of one parameter set: every subgrid of the cover is folded into every facet.
+
+    One step = ``add_new_subgrid_task`` for all subgrids in cover order (prepare_subgrid,
+    extract_from_subgrid(axis 0) per facet row, the fused subgrid_to_facets kernel, the fused
+    fold_column kernel whenever a subgrid column is complete) + ``finish()`` (finish_facet
+    along axis 0 for every facet).  The subgrid values do not influence the timing: ``n_inputs``
+    distinct random subgrids (2 GiB at N=65536, far larger than L2) are fed cyclically, which
+    keeps the 64 GiB a full set would need free for the 128 GiB of facet accumulators.
+    At N > 1 (:class:`SwiftlyBackwardSharded`) rank ``i % world`` supplies subgrid ``i``.
+    """
+
+    def __init__(self, params, device, rank=0, world=1, n_inputs=32):
+        self.params = dict(params)
+        self.device = device
+        self.rank = rank
+        self.world = world
+        self.cfg = SwiftlyConfig(device=device.index, **params)
+        self.core = self.cfg.core
+        self.facet_cfgs = make_full_facet_cover(self.cfg)
+        self.sg_cfgs = make_full_subgrid_cover(self.cfg)
+        self.xA = params["xA_size"]
+        gen = torch.Generator(device=device)
+        gen.manual_seed(987654321 + rank)
+        self.inputs = []
+        for _ in range(n_inputs):
+            t = torch.empty((self.xA, self.xA), dtype=torch.complex128, device=device)
+            torch.view_as_real(t).normal_(generator=gen)
+            self.inputs.append(t)
+        self.contributions_per_step = len(self.facet_cfgs) * len(self.sg_cfgs)
+        self.last_parts = None
+
+    def _barrier(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.device)
+
+    def step(self, timed=True, keep=False):
+        """One complete backward transform; returns ms (max over ranks)."""
+        self._barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        if self.world == 1:
+            bwd = SwiftlyBackward(self.cfg, self.facet_cfgs, lru_backward=1, queue_size=8)
+            for i, sg in enumerate(self.sg_cfgs):
+                bwd.add_new_subgrid_task(sg, self.inputs[i % len(self.inputs)])
+            ev[1].record()
+            tasks = bwd.finish()
+        else:
+            bwd = SwiftlyBackwardSharded(self.cfg, self.facet_cfgs, lru_backward=1, queue_size=8)
+            data = [self.inputs[i % len(self.inputs)] if i % self.world == self.rank else None
+                    for i in range(len(self.sg_cfgs))]
+            bwd.add_subgrid_tasks(self.sg_cfgs, data)
+            ev[1].record()
+            tasks = list(bwd.finish().values())
+        ev[2].record()
+        self._barrier()
+        ms = ev[0].elapsed_time(ev[2])
+        self.last_parts = (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]))
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        result = tasks if keep else None
+        del bwd, tasks
+        if not keep:
+            torch.cuda.empty_cache()
+        return (ms, result) if keep else (ms if timed else None)
+
+    def selfcheck(self, n_pixels=6, tol=5e-8):
+        """Parity of the path the timed steps ran: one more complete backward transform in which
+        ONE subgrid (middle of the cover) carries ``n_pixels`` non-zero samples and all others
+        are zero (they still run through every kernel).  The finished facets must then equal
+        the direct DFT of those samples, ``facet[x] = sum_u S[u] exp(-2 pi i u.x / N)`` times the
+        facet masks (the inverse of ``make_subgrid_from_sources``, fourier_algorithm.py:267-315;
+        SwiFTly reproduces it to its window accuracy: ~3e-9 for a
+        single-subgrid delta at W = 13.5625, measured with the reference algorithm).  A 192 x 192 corner block of up
+        to three local facets is compared; returns max|got - truth| / max|truth| over ranks."""
+        N, xA = self.params["N"], self.xA
+        rng = numpy.random.default_rng(424242)
+        i0 = len(self.sg_cfgs) // 2 + 5
+        sg = self.sg_cfgs[i0]
+        pix = [(int(rng.integers(xA)), int(rng.integers(xA)), complex(rng.random() + 0.5,
+                                                                      rng.random() - 0.5))
+               for _ in range(n_pixels)]
+        special = torch.zeros((xA, xA), dtype=torch.complex128, device=self.device)
+        for r0, r1, val in pix:
+            special[r0, r1] = val
+        zero = torch.zeros((xA, xA), dtype=torch.complex128, device=self.device)
+        saved = self.inputs
+        try:
+            class _Feed(list):  # input i of the step: the special subgrid at i0, zeros elsewhere
+                def __len__(self):
+                    return 1 << 40
+
+                def __getitem__(self, i):
+                    return special if i == i0 else zero
+
+            self.inputs = _Feed()
+            _, tasks = self.step(timed=True, keep=True)
+        finally:
+            self.inputs = saved
+        owner = partition_facets(self.facet_cfgs, self.world)
+        local = [i for i, o in enumerate(owner) if o == self.rank]
+        worst, checked, B = 0.0, 0, 192
+        for k in sorted({0, len(local) // 2, len(local) - 1}):
+            fc = self.facet_cfgs[local[k]]
+            got = tasks[k].tensor[:B, :B].cpu().numpy()
+            x0 = fc.off0 - fc.size // 2 + numpy.arange(B)
+            x1 = fc.off1 - fc.size // 2 + numpy.arange(B)
+            truth = numpy.zeros((B, B), dtype=complex)
+            for r0, r1, val in pix:
+                u0 = sg.off0 - xA // 2 + r0
+                u1 = sg.off1 - xA // 2 + r1
+                truth += val * numpy.exp(-2j * numpy.pi / N * (u0 * x0[:, None] + u1 * x1[None, :]))
+            if fc.mask0 is not None:
+                truth *= numpy.asarray(fc.mask0)[:B, None]
+            if fc.mask1 is not None:
+                truth *= numpy.asarray(fc.mask1)[None, :B]
+            worst = max(worst, float(numpy.abs(got - truth).max() / max(numpy.abs(truth).max(), 1e-300)))
+            checked += 1
+        del tasks
+        torch.cuda.empty_cache()
+        if self.world > 1:
+            t = torch.tensor([worst, float(checked)], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t[0:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
+            worst, checked = float(t[0].item()), int(t[1].item())
+        if not worst <= tol:
+            raise RuntimeError(f"backward self-check failed: max relative error {worst:.3e} "
+                               f"over {checked} facets exceeds {tol:g}")
+        return {"parity_max_rel_err": worst, "facets_checked": checked, "tolerance": tol,
+                "against": f"direct DFT of {n_pixels} non-zero samples of one subgrid (all other "
+                           "subgrids zero) on a 192 x 192 block of first / middle / last local "
+                           "facet; max|got - truth| / max|truth|"}
+
+    def kernel_rooflines(self, hbm_gbs):
+        """CUDA-event timings of the fused backward kernels in the shapes the step launches,
+        with their algorithmic bytes (compulsory reads + read-modify-write of the accumulators)."""
+        core, dev = self.core, self.device
+        p = self.params
+        yB, yN, xA, xM = p["yB_size"], p["yN_size"], p["xA_size"], p["xM_size"]
+        m = core.xM_yN_size
+        fcs = self.facet_cfgs
+        owner = partition_facets(fcs, self.world)
+        local = [i for i, o in enumerate(owner) if o == self.rank]
+        F = len(local)
+        S = len(self.sg_cfgs)
+        ncols = len({s.off0 for s in self.sg_cfgs})
+        rows = sorted({fcs[i].off0 for i in local})
+        sg = self.sg_cfgs[len(self.sg_cfgs) // 2 + 3]
+
+        def timeit(fn, reps=3):
+            fn()
+            torch.cuda.synchronize(dev)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+            evs[0].record()
+            for i in range(reps):
+                fn()
+                evs[i + 1].record()
+            torch.cuda.synchronize(dev)
+            return float(numpy.mean([evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]))
+
+        out = {}
+        x = self.inputs[0]
+        t = timeit(lambda: core.prepare_subgrid(x, (sg.off0, sg.off1)))
+        out["prepare_subgrid (both axes)"] = (t, 16.0 * (xA * xA + 2 * xM * xA + xM * xM), S)
+        prepared = core.prepare_subgrid(x, (sg.off0, sg.off1))
+        t = timeit(lambda: [core.extract_from_subgrid(prepared, o, axis=0) for o in rows])
+        out["extract_from_subgrid axis 0 (all local facet rows)"] = (
+            t, 16.0 * len(rows) * (m * xM + m * xM), S)
+        blocks = {o: core.extract_from_subgrid(prepared, o, axis=0) for o in rows}
+        accs = [torch.zeros((m, yN), dtype=torch.complex128, device=dev) for _ in local]
+        t = timeit(lambda: core.subgrid_to_facets(
+            [blocks[fcs[i].off0] for i in local], accs, [fcs[i].off1 for i in local], sg.off1))
+        out["subgrid_to_facets (extract axis 1 + accumulate, all local facets)"] = (
+            t, 16.0 * F * 3 * m * m, S)
+        faccs = [torch.zeros((yN, fcs[i].size), dtype=torch.complex128, device=dev)
+                 for i in local[:8]]
+        n8 = len(faccs)
+        t = timeit(lambda: core.fold_column(accs[:n8], faccs, [fcs[i].off1 for i in local[:n8]],
+                                            [None] * n8, sg.off0))
+        out[f"fold_column (finish axis 1 + add axis 0; timed on {n8} facets, scaled)"] = (
+            t * F / n8, 16.0 * F * (m * yN + 2 * m * yB), ncols)
+        t = timeit(lambda: core.finish_facet(faccs[0], fcs[local[0]].off0, fcs[local[0]].size, 0))
+        out["finish_facet axis 0"] = (t, 16.0 * (yN * yB + yB * yB), F)
+        kernels = []
+        total = sum(tt * n for tt, _, n in out.values())
+        for name, (tt, by, n) in out.items():
+            ach = by / (tt * 1e-3) / 1e9
+            kernels.append({"kernel": name, "avg_ms": tt, "launches_per_step": n,
+                            "algorithmic_bytes_per_launch": by, "achieved": ach, "unit": "GB/s",
+                            "frac": ach / hbm_gbs, "share_of_kernel_time": tt * n / total})
+        dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
+        return {"kernels": kernels,
+                "dominant": {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_gbs,
+                             "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                             "kernel": dom["kernel"], "avg_ms": dom["avg_ms"],
+                             "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}}

@@ -407,7 +407,9 @@ class SwiftlyCoreB200:
         """:meth:`sum_finish_axis` for several source groups in ONE launch.
 
         :param groups: list of source lists ``[(tensor, facet_off), ...]``
-        :param out: 3-D device tensor ``(n_groups, ...)``; ``out[g]`` receives group ``g``
+        :param out: 3-D device tensor ``(n_groups, ...)``; ``out[g]`` receives group ``g``.
+            With per-group ``subgrid_off`` it may also be a LIST of 2-D tensors of equal shape
+            and strides, one per group, living in different buffers (e.g. peer memory)
         :param subgrid_off: one offset, or a list with one offset per group (groups of
             different subgrids, e.g. a batch of the multi-GPU driver)
         :param mask: one mask (or None), or a list with one mask / None per group
@@ -448,8 +450,20 @@ class SwiftlyCoreB200:
     def _sum_finish_axis_batched(self, groups, out, axis, subgrid_offs, masks):
         if axis not in (0, 1):
             raise ValueError(f"Invalid axis {axis}")
+        scattered = isinstance(out, (list, tuple))  # one output buffer per group
+        if scattered:
+            outs = list(out)
+            if len(outs) != len(groups) or len(subgrid_offs) != len(groups):
+                raise ValueError("out / subgrid_off must have one entry per group")
+            for o in outs:
+                self._check_tensor(o)
+                if (o.dim() != 2 or tuple(o.shape) != tuple(outs[0].shape)
+                        or o.stride() != outs[0].stride() or o.dtype != torch.complex128):
+                    raise ValueError("scattered outputs must share shape, strides and dtype")
+            out = outs[0][None]
         self._check_tensor(out)
-        if out.dim() != 3 or out.shape[0] != len(groups) or len(subgrid_offs) != len(groups):
+        if out.dim() != 3 or (not scattered and out.shape[0] != len(groups)) \
+                or len(subgrid_offs) != len(groups):
             raise ValueError("out / subgrid_off must have one entry per group")
         if masks is None:
             masks = [None] * len(groups)
@@ -479,6 +493,13 @@ class SwiftlyCoreB200:
                 keep.append(mk)
                 mptrs[g] = mk.data_ptr()
         dout = self._describe(out[0], axis)
+        if scattered:
+            ptrs = (ctypes.c_void_p * len(groups))(*[o.data_ptr() for o in outs])
+            rc = self._lib.swiftly_b200_sum_finish_axis_scattered(
+                self._plan, arr, sizes, len(groups), ctypes.byref(dout), ptrs, offs, mptrs,
+                self._stream(outs[0]))
+            _lib.check(self._lib, rc)
+            return outs
         rc = self._lib.swiftly_b200_sum_finish_axis_batched(
             self._plan, arr, sizes, len(groups), ctypes.byref(dout), int(out.stride(0)),
             offs, mptrs, self._stream(out))
@@ -523,6 +544,22 @@ class SwiftlyCoreB200:
         )
         _lib.check(self._lib, rc)
         return out
+
+    # ------------------------------------------------------------------ rank-to-rank ordering
+    def peer_signal(self, flag_table, n_peers, my_rank, value, stream_of):
+        """Store ``value`` into entry ``my_rank`` of every rank's flag array (peer_sync.cu).
+        ``flag_table``: int64 device tensor holding this rank's mappings of the arrays."""
+        rc = self._lib.swiftly_b200_peer_signal(
+            self._plan, ctypes.c_void_p(flag_table.data_ptr()), int(n_peers), int(my_rank),
+            int(value), self._stream(stream_of))
+        _lib.check(self._lib, rc)
+
+    def peer_wait(self, my_flags, n_peers, value, status, timeout_s=20.0):
+        """Make the stream wait until all ``n_peers`` entries of ``my_flags`` are >= value."""
+        rc = self._lib.swiftly_b200_peer_wait(
+            self._plan, ctypes.c_void_p(my_flags.data_ptr()), int(n_peers), int(value),
+            float(timeout_s), ctypes.c_void_p(status.data_ptr()), self._stream(my_flags))
+        _lib.check(self._lib, rc)
 
     # ------------------------------------------------------------------ fused backward path
     def _lines_array(self, tensors, shape_check):

@@ -53,7 +53,7 @@ static int sum_finish_groups(const swiftly_b200* h, const swiftly_b200_source* s
                              const int32_t* group_sizes, int n_groups,
                              const swiftly_b200_lines* out, int64_t out_group_stride,
                              const int64_t* subgrid_offs, const double* const* masks,
-                             void* stream) {
+                             void* stream, void* const* out_ptrs = nullptr) {
     if (!h || !sources || !out || !group_sizes) return einval("sum_finish_axis: NULL argument");
     if (out->location != SWIFTLY_B200_DEVICE) return einval("sum_finish_axis: device arrays only");
     const int64_t yN = h->yN, xM = h->xM, m = h->m;
@@ -164,7 +164,9 @@ static int sum_finish_groups(const swiftly_b200* h, const swiftly_b200_source* s
             const int gg = g < ng ? g0 + g : g0;
             a.start[g] = (int)pmod(xM / 2 - sz / 2 + subgrid_offs[gg], xM);
             a.mask[g] = masks ? masks[gg] : nullptr;
+            a.out_g[g] = (out_ptrs && g < ng) ? (cplx*)out_ptrs[gg] : nullptr;
         }
+        if (out_ptrs) a.out = (cplx*)out_ptrs[g0];
         return run_subgrid_axis(h, a, (cudaStream_t)stream);
     };
 
@@ -223,6 +225,24 @@ extern "C" int swiftly_b200_sum_finish_axis_batched(const swiftly_b200* h,
     if (!subgrid_offs) return einval("sum_finish_axis: NULL subgrid offsets");
     return sum_finish_groups(h, sources, group_sizes, n_groups, out, out_group_stride,
                              subgrid_offs, masks, stream);
+}
+
+// Groups whose outputs live in DIFFERENT buffers (same shape and strides): out_ptrs[g] is the
+// base of group g's output, `out` describes shape and strides.  The multi-GPU driver passes
+// the peers' receive buffers here: the strips leave the kernel straight into the owner's
+// memory over NVLink (bulk tensor stores of the TMA engine, or plain stores).
+extern "C" int swiftly_b200_sum_finish_axis_scattered(const swiftly_b200* h,
+                                                      const swiftly_b200_source* sources,
+                                                      const int32_t* group_sizes, int n_groups,
+                                                      const swiftly_b200_lines* out,
+                                                      void* const* out_ptrs,
+                                                      const int64_t* subgrid_offs,
+                                                      const double* const* masks, void* stream) {
+    if (!subgrid_offs || !out_ptrs) return einval("sum_finish_axis: NULL argument");
+    for (int g = 0; g < n_groups; ++g)
+        if (!out_ptrs[g]) return einval("sum_finish_axis: NULL output pointer");
+    return sum_finish_groups(h, sources, group_sizes, n_groups, out, 0, subgrid_offs, masks,
+                             stream, out_ptrs);
 }
 
 extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,

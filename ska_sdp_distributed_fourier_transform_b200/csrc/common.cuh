@@ -109,6 +109,7 @@ struct TensorMap4 {
     int64_t stride[4];  // in doubles
     int64_t dim[4];
     int box[4];
+    int swizzle128;  // loads: destination tile written with the 128-byte swizzle pattern
 };
 #else
 struct alignas(64) TensorMap4 {
@@ -162,6 +163,19 @@ struct DeviceCtx {
             "DONE_%=:\n"
             "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
     }
+    // ---- bulk tensor loads (TMA): strided global tile -> shared memory tile, completion on
+    // an mbarrier.  Box at coordinates (0, c1, c2, 0) of a rank-4 map; with a 128-byte swizzled
+    // map the 16-byte unit u of 128-byte row c of the tile lands at unit (u ^ (c & 7)): strided
+    // reads of the tile (every 2nd / 4th sample) are then free of bank conflicts.  The
+    // destination must be 1024-byte aligned.
+    __device__ __forceinline__ void tensor_load(void* smem_dst, const void* map, int c1, int c2,
+                                                uint64_t* bar) const {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(0), "r"(c1),
+              "r"(c2), "r"(0), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+    }
     // ---- bulk tensor stores (TMA): shared memory tile -> strided global tile ----
     // ordinary shared-memory writes become visible to the asynchronous proxy
     __device__ __forceinline__ void fence_async() const {
@@ -183,6 +197,10 @@ struct DeviceCtx {
     __device__ __forceinline__ void bulk_wait_read() const {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    // ... have completed entirely (their global writes are performed)
+    __device__ __forceinline__ void bulk_wait_all() const {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
     // bulk L2 prefetch of a contiguous global region (no registers, no LSU wavefronts)
     __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) const {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes)
@@ -190,7 +208,7 @@ struct DeviceCtx {
     }
 };
 
-extern __shared__ __align__(16) char swiftly_dyn_smem[];
+extern __shared__ __align__(1024) char swiftly_dyn_smem[];
 
 // register budget: at least 512 resident threads per SM (<= 128 registers/thread)
 template <class Body>

@@ -17,6 +17,31 @@ static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op,
     k.tw2 = SPLIT ? twiddles_full(h, 2 * H) : nullptr;
     if (!k.tw || (SPLIT && !k.tw2)) return SWIFTLY_B200_ECUDA;
     k.in_cap = (max_fs + 1) & ~1;
+    // swizzled tensor loads when every facet row is whole 128-byte chunks (sg_variant 6: linear)
+    const int n_facets = (int)(op.g.n_lines / op.lines_per);
+    k.swizzled = h->sg_variant != 6 ? 1 : 0;
+    k.box_chunks = 8;
+    for (int f = 0; f < n_facets && k.swizzled; ++f)
+        if (op.fac[f].fs % 8 != 0 || op.fac[f].in_ls < op.fac[f].fs) k.swizzled = 0;
+    if (k.swizzled) {
+        int chunks = max_fs / 8;
+        k.box_chunks = chunks >= 256 ? 256 : (chunks & ~7);
+        if (k.box_chunks < 8) k.swizzled = 0;
+    }
+    if (k.swizzled) {
+        // staging capacity: whole boxes
+        const int boxes = (max_fs / 8 + k.box_chunks - 1) / k.box_chunks;
+        k.in_cap = boxes * k.box_chunks * 8;
+        for (int f = 0; f < n_facets && k.swizzled; ++f)
+            if (!make_row_map(&k.in_map[f], op.fac[f].in, op.fac[f].in_ls, op.n, op.fac[f].fs,
+                              k.box_chunks))
+                k.swizzled = 0;
+        if (!k.swizzled) k.in_cap = (max_fs + 1) & ~1;
+    }
+    if (K::smem_bytes(k.in_cap) > (size_t)227 * 1024) {
+        k.swizzled = 0;
+        k.in_cap = (max_fs + 1) & ~1;
+    }
     const size_t smem = K::smem_bytes(k.in_cap);
     int per_sm = (int)((size_t)227 * 1024 / smem);
     if (per_sm > 512 / K::THREADS) per_sm = 512 / K::THREADS;
@@ -30,6 +55,54 @@ static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op,
     }
     cudaError_t e = launch_body(k, (int)blocks, smem, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "extract_columns (TMA) kernel launch");
+}
+
+// 4 x Q split with two thread groups (extract_tma.cuh)
+template <int Q>
+static int launch_extract_tma4(const swiftly_b200* h, const ExtractColumnsOp& op, int max_fs,
+                               cudaStream_t s) {
+    typedef ExtractColumnsTma4Kernel<Q> K;
+    K k;
+    k.op = op;
+    k.tw = twiddles(h, Q);
+    k.twf = twiddles_full(h, 4 * Q);
+    if (!k.tw || !k.twf) return SWIFTLY_B200_ECUDA;
+    const int n_facets = (int)(op.g.n_lines / op.lines_per);
+    k.in_cap = (max_fs + 1) & ~1;
+    k.swizzled = h->sg_variant != 6 ? 1 : 0;
+    k.box_chunks = 8;
+    for (int f = 0; f < n_facets && k.swizzled; ++f)
+        if (op.fac[f].fs % 8 != 0 || op.fac[f].in_ls < op.fac[f].fs) k.swizzled = 0;
+    if (k.swizzled) {
+        int chunks = max_fs / 8;
+        k.box_chunks = chunks >= 256 ? 256 : (chunks & ~7);
+        if (k.box_chunks < 8) k.swizzled = 0;
+    }
+    if (k.swizzled) {
+        const int boxes = (max_fs / 8 + k.box_chunks - 1) / k.box_chunks;
+        k.in_cap = boxes * k.box_chunks * 8;
+        for (int f = 0; f < n_facets && k.swizzled; ++f)
+            if (!make_row_map(&k.in_map[f], op.fac[f].in, op.fac[f].in_ls, op.n, op.fac[f].fs,
+                              k.box_chunks))
+                k.swizzled = 0;
+        if (!k.swizzled) k.in_cap = (max_fs + 1) & ~1;
+    }
+    if (K::smem_bytes(k.in_cap) > (size_t)227 * 1024) {
+        k.swizzled = 0;
+        k.in_cap = (max_fs + 1) & ~1;
+    }
+    const size_t smem = K::smem_bytes(k.in_cap);
+    if (smem > (size_t)227 * 1024) return -1;
+    int per_sm = (int)((size_t)227 * 1024 / smem);
+    if (per_sm > 512 / K::THREADS) per_sm = 512 / K::THREADS;  // 128 registers per thread
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)148 * per_sm;
+    if (blocks > op.g.n_lines) blocks = op.g.n_lines;
+    k.scratch = split_scratch(h, s, (size_t)blocks * 4 * Q);
+    if (!k.scratch) return SWIFTLY_B200_ECUDA;
+    cudaError_t e = launch_body(k, (int)blocks, smem, s);
+    return e == cudaSuccess ? SWIFTLY_B200_OK
+                            : cuda_fail(e, "extract_columns (TMA, 4-way split) kernel launch");
 }
 
 // returns -1 when the TMA-staged kernel does not apply (then the generic kernels run)
@@ -47,6 +120,25 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
     if ((size_t)((max_fs + 1) & ~1) * 16 + (size_t)(hh + hh / 16) * 8 + 16 > (size_t)227 * 1024)
         return -1;
     if (split) {
+        // 4 x (n/4) with two thread groups (default for 16384; sg_variant 7 / force_split 1:
+        // the 2 x (n/2) kernel)
+        if (h->sg_variant != 7 && h->force_split != 1) {
+            switch (n) {
+                case 16384: {
+                    int rc = launch_extract_tma4<4096>(h, op, max_fs, s);
+                    if (rc != -1) return rc;
+                    break;
+                }
+#if defined(SWIFTLY_EMU)
+                case 512: {
+                    int rc = launch_extract_tma4<128>(h, op, max_fs, s);
+                    if (rc != -1) return rc;
+                    break;
+                }
+#endif
+                default: break;
+            }
+        }
         switch (n) {
             case 16384: return launch_extract_tma<8192, true>(h, op, max_fs, s);
 #if defined(SWIFTLY_EMU)

@@ -23,6 +23,7 @@ static int launch_sg_axis_l(const swiftly_b200* h, const SubgridAxisArgs& a, cud
     for (int g = 0; g < SW_MAX_GROUPS; ++g) {
         k.start[g] = a.start[g];
         k.mask[g] = a.mask[g];
+        k.out_g[g] = a.out_g[g];
     }
     k.scale = 1.0 / (double)XM;
     k.first_round_tiles = a.first_round_tiles;
@@ -51,6 +52,7 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
     for (int g = 0; g < SW_MAX_GROUPS; ++g) {
         k.start[g] = a.start[g];
         k.mask[g] = a.mask[g];
+        k.out_g[g] = a.out_g[g];
     }
     k.scale = 1.0 / (double)XM;
     k.first_round_tiles = a.first_round_tiles;
@@ -60,14 +62,24 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
     k.tma_out = 0;
     k.tma_box = a.sz < 256 ? a.sz : 256;
     k.tma_slot_line = k.tma_slot_elem = k.tma_slot_group = 1;
+    k.tma_per_group = a.out_g[0] != nullptr ? 1 : 0;
     // (the last box may be partial: the engine still reads a whole box from shared memory)
     const size_t staged = (size_t)((a.sz + k.tma_box - 1) / (k.tma_box > 0 ? k.tma_box : 1)) *
                           (size_t)k.tma_box * sizeof(cplx);
     if (!a.accumulate_out && h->sg_variant != 5 && a.sz >= 1 &&
         staged <= (size_t)k.WORK * sizeof(double)) {
         int slot[3];
-        if (make_out_map(&k.out_map, a.out, a.out_ls, a.out_es, a.out_gs, a.n_lines, a.sz,
-                         a.n_groups, k.tma_box, slot)) {
+        bool ok = true;
+        if (k.tma_per_group) {
+            // (the slots depend on the strides only, which all groups share)
+            for (int g = 0; g < a.n_groups && ok; ++g)
+                ok = make_out_map(&k.out_map[g], a.out_g[g], a.out_ls, a.out_es, 0, a.n_lines,
+                                  a.sz, 1, k.tma_box, slot);
+        } else {
+            ok = make_out_map(&k.out_map[0], a.out, a.out_ls, a.out_es, a.out_gs, a.n_lines,
+                              a.sz, a.n_groups, k.tma_box, slot);
+        }
+        if (ok) {
             k.tma_out = 1;
             k.tma_slot_line = slot[0];
             k.tma_slot_elem = slot[1];
@@ -87,7 +99,7 @@ struct PingPongFits {
     static constexpr bool V = (XM / M) <= 4;
 #else
     static constexpr bool V = (XM / M) <= 4 && (XM / 16) % 32 == 0 &&
-                              2 * ((size_t)(XM + XM / 16) * 16 + (size_t)(XM + XM / 16 + 8) * 8) <=
+                              2 * ((size_t)(XM + XM / 16) * 16 + (size_t)(XM + XM / 16 + 24) * 8) <=
                                   227 * 1024;
 #endif
 };

@@ -38,6 +38,12 @@ struct ExtractColumnsTmaKernel {
     const cplx* tw2;  // exp(-2 pi i t / 2H), t < H (SPLIT only)
     cplx* scratch;    // gridDim.x * H samples (SPLIT only)
     int in_cap;       // capacity of the staging buffer in samples (>= every facet's fs, even)
+    // rows staged by bulk TENSOR loads with the 128-byte swizzle (tensor_map.cu make_row_map):
+    // the E / O transforms read every second sample of the row -- 32-byte stride, a 2-way
+    // bank conflict on a linear buffer, conflict free on the swizzled one
+    int swizzled;
+    int box_chunks;  // 128-byte chunks per tensor load
+    TensorMap4 in_map[SW_MAX_COLUMN_FACETS];
 
     // first-pass loads must be done before the staging buffer is refilled: the refill is issued
     // by thread 0 right after the first barrier that follows them
@@ -64,6 +70,15 @@ struct ExtractColumnsTmaKernel {
         const int l = (int)(line - (int64_t)f * op.lines_per);
         const ColumnFacet& F = op.fac[f];
         const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
+        if (swizzled) {
+            const int chunks = F.fs / 8;
+            const int boxes = (chunks + box_chunks - 1) / box_chunks;
+            // (a box that sticks out of the row is zero filled and still counts in full)
+            ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
+            for (int c0 = 0; c0 < chunks; c0 += box_chunks)
+                ctx.tensor_load((char*)in + (size_t)c0 * 128, &in_map[f], c0, (int)row, bar);
+            return;
+        }
         const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
         ctx.tx_expect(bar, bytes);
         // one bulk copy may not exceed the engine's size field comfortably: 64 KiB pieces
@@ -97,11 +112,13 @@ struct ExtractColumnsTmaKernel {
             const double* fb = op.fb + F.fb_off;
             cplx* o = F.out + (int64_t)l * F.out_ls;
             const double scale = op.scale;
+            const bool swz = swizzled != 0;
             // natural-order input sample q of the zero-padded, rotated, Fb-weighted row
             auto sample = [&](int q) {
                 int k = wrap_add(q, shift_in, n);
                 if (k >= fs) return mk(0.0, 0.0);
-                return cscale(in[k], ldg_d(fb + k));
+                const int ks = swz ? ((k & ~7) | ((k ^ (k >> 3)) & 7)) : k;
+                return cscale(in[ks], ldg_d(fb + k));
             };
             auto put = [&](int p, cplx v) {
                 int pc = wrap_add(p, n / 2, n);
@@ -137,6 +154,161 @@ struct ExtractColumnsTmaKernel {
                 line_fft<H, DIR>(lt, sm, tw, ld, put, refill);
             }
             ctx.sync();  // exchange buffer is reused by the next line
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// yN = 4 Q: the line as FOUR Q-point transforms (decimation in time by 4), two thread groups.
+//
+//   e_q[j] = z[4 j + q],  E_q = FFT_Q(e_q),  t_q[k] = w^(q k) E_q[k],  w = exp(+2 pi i / yN)
+//   X[k + Q s] = sum_q t_q[k] (+i)^(q s)                      (radix-4 butterfly over q)
+//
+// Compared with the 2 x (yN/2) split above: a Q = 4096 point transform needs two exchanges
+// instead of three (a third less shared-memory traffic for the same samples), and -- more
+// important -- the CTA is TWO independent groups of Q/16 threads, each with its own exchange
+// buffer and named barrier, working on different sub-transforms of the SAME staged row
+// (group g: q = 2g, 2g + 1): their exchange (LSU) and butterfly (FP64) phases drift apart and
+// overlap, where 512 threads in lockstep leave one pipe idle while the other works.  The
+// stride-4 reads of the staged row are conflict free thanks to the 128-byte swizzle.  All
+// four t_q are parked in a per-CTA scratch (L2 resident); after a CTA barrier every thread
+// combines its share of the k range and writes four unit-stride output streams.
+template <int Q>
+struct ExtractColumnsTma4Kernel {
+    static constexpr int DIR = +1;
+    static constexpr int TG = FftCfg<Q>::T;  // threads per group
+    static constexpr int THREADS = 2 * TG;
+    static constexpr int N = 4 * Q;
+    static constexpr int XBUF = (FftCfg<Q>::PADDED + 1) & ~1;  // doubles per exchange buffer
+    static constexpr size_t smem_bytes(int in_cap) {
+        return (size_t)in_cap * sizeof(cplx) + 2 * (size_t)XBUF * sizeof(double) + 32;
+    }
+
+    ExtractColumnsOp op;
+    const cplx* tw;   // compact table of the Q-point plan
+    const cplx* twf;  // exp(-2 pi i t / yN), t < yN / 2
+    cplx* scratch;    // gridDim.x * 4 Q samples
+    int in_cap;
+    int swizzled;
+    int box_chunks;
+    TensorMap4 in_map[SW_MAX_COLUMN_FACETS];
+
+    SW_HD cplx root(int t) const {  // exp(DIR 2 pi i t / N), 0 <= t < N
+        const bool neg = t >= N / 2;
+        cplx w = ldg_c(twf + (neg ? t - N / 2 : t));
+        if (DIR > 0) w.y = -w.y;
+        return neg ? mk(-w.x, -w.y) : w;
+    }
+
+    template <class Ctx>
+    SW_HD void issue(const Ctx& ctx, cplx* in, uint64_t* bar, int64_t line) const {
+        const int f = (int)(line / op.lines_per);
+        const int l = (int)(line - (int64_t)f * op.lines_per);
+        const ColumnFacet& F = op.fac[f];
+        const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
+        if (swizzled) {
+            const int chunks = F.fs / 8;
+            const int boxes = (chunks + box_chunks - 1) / box_chunks;
+            ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
+            for (int c0 = 0; c0 < chunks; c0 += box_chunks)
+                ctx.tensor_load((char*)in + (size_t)c0 * 128, &in_map[f], c0, (int)row, bar);
+            return;
+        }
+        const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
+        ctx.tx_expect(bar, bytes);
+        const char* src = (const char*)(F.in + row * F.in_ls);
+        for (uint32_t o = 0; o < bytes; o += 65536u)
+            ctx.tx_copy((char*)in + o, src + o, bytes - o < 65536u ? bytes - o : 65536u, bar);
+    }
+
+    // group barrier; after the first-pass loads of the group's LAST sub-transform the staging
+    // buffer is dead for this group: the second group to get there starts the next row's copy
+    template <class Ctx>
+    struct GroupSync {
+        const Ctx& ctx;
+        const ExtractColumnsTma4Kernel& k;
+        int grp, tg;
+        cplx* in;
+        uint64_t* bar;
+        int* done;  // shared counter
+        int64_t next_line;
+        bool pending;
+        SW_HD void operator()() {
+            ctx.group_sync(1 + grp, TG);
+            if (pending) {
+                pending = false;
+                if (tg == 0) {
+#if defined(__CUDA_ARCH__)
+                    const int prev = atomicAdd(done, 1);
+#else
+                    const int prev = (*done)++;
+#endif
+                    if ((prev & 1) == 1 && next_line < k.op.g.n_lines)
+                        k.issue(ctx, in, bar, next_line);
+                }
+            }
+        }
+    };
+
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        cplx* in = (cplx*)ctx.smem;
+        double* xb = (double*)(in + in_cap);
+        uint64_t* bar = (uint64_t*)(xb + 2 * XBUF);
+        int* done = (int*)(bar + 1);
+        const int grp = ctx.tid / TG;
+        const int tg = ctx.tid % TG;
+        double* sm = xb + (size_t)grp * XBUF;
+        cplx* stash = scratch + (size_t)ctx.bid * N;
+        const int n = op.n;
+        if (ctx.tid == 0) {
+            ctx.tx_init(bar);
+            *done = 0;
+            if ((int64_t)ctx.bid < op.g.n_lines) issue(ctx, in, bar, ctx.bid);
+        }
+        ctx.sync();
+        uint32_t parity = 0;
+        for (int64_t line = ctx.bid; line < op.g.n_lines; line += ctx.nblocks) {
+            const int f = (int)(line / op.lines_per);
+            const int l = (int)(line - (int64_t)f * op.lines_per);
+            const ColumnFacet& F = op.fac[f];
+            const int shift_in = F.shift_in, fs = F.fs;
+            const double* fb = op.fb + F.fb_off;
+            cplx* o = F.out + (int64_t)l * F.out_ls;
+            const double scale = op.scale;
+            const bool swz = swizzled != 0;
+            auto sample = [&](int q) {
+                int k = wrap_add(q, shift_in, n);
+                if (k >= fs) return mk(0.0, 0.0);
+                const int ks = swz ? ((k & ~7) | ((k ^ (k >> 3)) & 7)) : k;
+                return cscale(in[ks], ldg_d(fb + k));
+            };
+            ctx.tx_wait(bar, parity);
+            parity ^= 1;
+            GroupSync<Ctx> gs{ctx, *this, grp, tg, in, bar, done, line + ctx.nblocks, false};
+#pragma unroll 1
+            for (int qi = 0; qi < 2; ++qi) {
+                const int q4 = 2 * grp + qi;
+                cplx* sq = stash + (size_t)q4 * Q;
+                auto ld = [&](int j) { return sample(4 * j + q4); };
+                auto st = [&](int k, cplx v) { sq[k] = q4 ? cmul(v, root(q4 * k)) : v; };
+                gs.pending = (qi == 1);
+                line_fft<Q, DIR>(tg, sm, tw, ld, st, gs);
+                gs();  // the group's exchange buffer is reused by its next sub-transform
+            }
+            ctx.sync();  // all four t_q are in the scratch
+            for (int k = ctx.tid; k < Q; k += THREADS) {
+                cplx t[4];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) t[q4] = stash[(size_t)q4 * Q + k];
+                Radix<4, DIR>::run(t);
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    int pc = wrap_add(k + Q * s4, n / 2, n);
+                    st_stream(o + pc, cscale(t[s4], scale));
+                }
+            }
+            ctx.sync();  // scratch and exchange buffers are reused by the next line
         }
     }
 };

@@ -615,6 +615,7 @@ struct SubgridAxisKernel {
     // the launch is a later piece of a job with more sources than fit one launch: the
     // finished lines are ADDED to `out` (finishing is linear)
     int accumulate_out;
+    cplx* out_g[SW_MAX_GROUPS];  // optional per-group output base (null: out + g * out_gs)
 
     template <class Ctx>
     SW_HD void operator()(Ctx& ctx) const {
@@ -707,7 +708,7 @@ struct SubgridAxisKernel {
                 ctx.sync();
             }
             {
-                cplx* o = out + (int64_t)grp * out_gs + line * out_ls;
+                cplx* o = (out_g[grp] ? out_g[grp] : out + (int64_t)grp * out_gs) + line * out_ls;
                 const int gstart = start[grp];
                 const double* gmask = mask[grp];
                 auto ld = [&](int q) { return acc[wrap_add(q, XM / 2, XM)]; };

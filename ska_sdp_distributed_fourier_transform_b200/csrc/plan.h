@@ -68,11 +68,18 @@ struct SubgridAxisArgs {
     const double* mask[SW_MAX_GROUPS];
     int first_round_tiles;
     int accumulate_out;  // add to `out` instead of overwriting it (later pieces of a split job)
+    // optional per-group output base pointers (groups that live in DIFFERENT allocations,
+    // e.g. the peers' receive buffers of the multi-GPU driver); null: out + g * out_gs
+    cplx* out_g[SW_MAX_GROUPS];
 };
 // rank-4 tensor map over an output array with arbitrary line / sample / group strides
 // (tensor_map.cu); slot[0..2] receive the coordinate slots of line / sample / group
 bool make_out_map(TensorMap4* tm, cplx* out, int64_t out_ls, int64_t out_es, int64_t out_gs,
                   int64_t n_lines, int64_t sz, int64_t n_groups, int box_rows, int* slot);
+
+// rank-4 map for staging rows of a complex128 array in shared memory, 128-byte swizzled
+bool make_row_map(TensorMap4* tm, const cplx* base, int64_t ls, int64_t n_rows, int64_t fs,
+                  int box_chunks);
 
 // returns SWIFTLY_B200_EUNSUPPORTED (without setting up anything) when the (m, xM) pair has no
 // fused instantiation; conc_out receives the number of sources processed concurrently

@@ -32,7 +32,9 @@ struct SubgridAxisKernelPP {
     static constexpr int CONC = T_X / T_M;  // concurrent m-point transforms per line
     static_assert(CONC >= 1 && CONC <= 4, "at most four concurrent m-point transforms");
     static constexpr int WSTRIDE = FftCfg<M>::PADDED | 1;
-    static constexpr int WORK = (CONC * WSTRIDE + 1) & ~1;  // doubles per group
+    // doubles per group; a multiple of 128 bytes: the work area doubles as the staging buffer of
+    // the bulk tensor stores, whose shared-memory address must be 128-byte aligned
+    static constexpr int WORK = (CONC * WSTRIDE + 15) & ~15;
     static constexpr int ACCS = XM + XM / 16;  // cplx per group: accumulator / xM exchange
     static constexpr size_t SMEM =
         (size_t)GROUPS * ((size_t)ACCS * sizeof(cplx) + (size_t)WORK * sizeof(double));
@@ -63,7 +65,9 @@ struct SubgridAxisKernelPP {
     int tma_out;
     int tma_box;                                       // samples per bulk tensor store
     int tma_slot_line, tma_slot_elem, tma_slot_group;  // coordinate slots (1..3)
-    TensorMap4 out_map;
+    int tma_per_group;                 // one tensor map per group (groups in different buffers)
+    cplx* out_g[SW_MAX_GROUPS];        // optional per-group output base (null: out + g * out_gs)
+    TensorMap4 out_map[SW_MAX_GROUPS];  // [0] covers all groups unless tma_per_group
 
     // barrier ids: 0 = whole CTA, 1 + g = group g, 3 + g * CONC + c = transform c of group g,
     // 11 + g = token of group g
@@ -144,9 +148,12 @@ struct SubgridAxisKernelPP {
                         acc[pos] = mk(a.x + f * v.x, a.y + f * v.y);
                     }
                 };
-                // L2 prefetch of what this thread loads next: the next round of this line, or
-                // the first round of the group's next line
-                {
+                // L2 prefetch of what this transform loads next -- the next round of this line, or
+                // the first round of the group's next line: ONE bulk prefetch per window
+                // (cp.async.bulk.prefetch.L2, issued by the transform's first thread; the window
+                // is M contiguous samples, in two pieces when it wraps), no per-thread
+                // prefetch instructions and no LSU wavefronts
+                if (lt == 0) {
                     int pslot0 = slot0 + CONC, psgrp = sgrp;
                     int64_t pline = line;
                     if (pslot0 >= n_slots) {
@@ -160,12 +167,11 @@ struct SubgridAxisKernelPP {
                         const SgSource& ps = src[psgrp * n_slots + pslot0 + c];
                         if (ps.base != nullptr && ps.es == 1) {
                             const cplx* pb = ps.base + pline * ps.ls;
-#pragma unroll
-                            for (int r = 0; r < 16; ++r) {
-                                int tc = wrap_add(lt + r * T_M, M / 2, M);
-                                int idx = wrap_add(ps.wbase, wrap_sub(tc, ps.s_m, M), ps.wmod);
-                                prefetch_l2(pb + (int64_t)idx * ps.es);
-                            }
+                            const int first = ps.wbase;  // samples [first, first + M) mod wmod
+                            const int n1 = first + M <= ps.wmod ? M : ps.wmod - first;
+                            ctx.bulk_prefetch_l2(pb + first, (uint32_t)n1 * (uint32_t)sizeof(cplx));
+                            if (n1 < M)
+                                ctx.bulk_prefetch_l2(pb, (uint32_t)(M - n1) * (uint32_t)sizeof(cplx));
                         }
                     }
                 }
@@ -173,7 +179,7 @@ struct SubgridAxisKernelPP {
                 gsync();  // accumulator complete; work buffers free
             }
             {
-                cplx* o = out + (int64_t)sgrp * out_gs + line * out_ls;
+                cplx* o = (out_g[sgrp] ? out_g[sgrp] : out + (int64_t)sgrp * out_gs) + line * out_ls;
                 const int gstart = start[sgrp];
                 const double* gmask = mask[sgrp];
                 auto ld = [&](int q) { return acc[wrap_add(q, XM / 2, XM)]; };
@@ -203,15 +209,17 @@ struct SubgridAxisKernelPP {
                 ctx.fence_async();
                 int c[4] = {0, 0, 0, 0};
                 c[tma_slot_line] = (int)line;
-                c[tma_slot_group] = sgrp;
+                c[tma_slot_group] = tma_per_group ? 0 : sgrp;
+                const TensorMap4* map = &out_map[tma_per_group ? sgrp : 0];
                 for (int r0 = 0; r0 < sz; r0 += tma_box) {
                     c[tma_slot_elem] = r0;
-                    ctx.tensor_store(&out_map, (const cplx*)work + r0, c[1], c[2], c[3]);
+                    ctx.tensor_store(map, (const cplx*)work + r0, c[1], c[2], c[3]);
                 }
                 ctx.bulk_commit();
             }
         }
-        if (tma_out && t == 0) ctx.bulk_wait_read();
+        // the strips may go to a peer GPU: the kernel ends only when the bulk stores are performed
+        if (tma_out && t == 0) ctx.bulk_wait_all();
         // consume group 1's last release so that every barrier ends balanced
         if (TOKENS && grp == 0) ctx.group_sync(11, THREADS);
     }

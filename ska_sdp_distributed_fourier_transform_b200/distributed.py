@@ -128,14 +128,24 @@ class SwiftlyForwardSharded:
             symm_mem.enable_symm_mem_for_group(grp.group_name)
         except Exception:  # pylint: disable=broad-except
             pass  # newer torch enables it lazily
-        self._symm = {"mod": symm_mem, "group": grp, "slots": {}}
+        key = (grp.group_name, self.device.index, self.world, self.rows_max,
+               self.core.xM_yN_size)
+        if key not in self._SYMM_CACHE:
+            self._SYMM_CACHE[key] = {"mod": symm_mem, "group": grp, "slots": {}}
+        self._symm = self._SYMM_CACHE[key]
+
+    N_SLOTS = 4  # see _run_p2p: a slot is rewritten four batches later
+    # symmetric buffers are expensive to set up (a rendezvous over the group) and identical
+    # for every transform of a geometry: they are kept per (group, device) across instances
+    _SYMM_CACHE = {}
 
     def _symm_slots(self, xA):
-        """(handle, [per-rank views of both slots]) for subgrid size ``xA``."""
+        """(handle, [per-rank views of all slots]) for subgrid size ``xA``."""
         st = self._symm
         if xA not in st["slots"]:
             m = self.core.xM_yN_size
-            shape = (2, self.world, self.rows_max, xA, m)  # strips transposed, see api.py
+            # strips transposed (contribution index contiguous), see api.py
+            shape = (self.N_SLOTS, self.world, self.rows_max, xA, m)
             n = 1
             for d in shape:
                 n *= d
@@ -148,6 +158,25 @@ class SwiftlyForwardSharded:
                 views.append(torch.view_as_complex(peer.view(n, 2)).view(shape).transpose(3, 4))
             st["slots"][xA] = (hdl, views, buf)
         return st["slots"][xA]
+
+    def _symm_flags(self):
+        """Per-rank flag arrays (int64[world]) in symmetric memory: (table of my mappings of
+        every rank's array, my own array, status word)."""
+        st = self._symm
+        if "flags" not in st:
+            buf = st["mod"].empty(self.world, dtype=torch.int64, device=self.device)
+            buf.zero_()
+            hdl = st["mod"].rendezvous(buf, group=st["group"])
+            maps = [hdl.get_buffer(r, (self.world,), torch.int64, 0) for r in range(self.world)]
+            table = torch.tensor([t.data_ptr() for t in maps], dtype=torch.int64,
+                                 device=self.device)
+            status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            hdl.barrier(channel=0)  # everybody's flags are zero before anybody signals
+            st["flags"] = (hdl, maps, table, buf, status)
+            st["seq"] = 0
+        return st["flags"]
 
     # ------------------------------------------------------------------ local stages
     def _prepare(self):
@@ -308,23 +337,70 @@ class SwiftlyForwardSharded:
         finish(*pending)
         return results
 
+    def _local_strips_batch_p2p(self, batch, views, slot):
+        """Axis-1 reduction for all subgrids of a batch, the strips of subgrid ``b`` going
+        straight into the receive slot of its owner (rank ``b``) over NVLink: ONE launch per run
+        of subgrids that share the subgrid column, every group with its own output buffer."""
+        if not self.my_rows:
+            return
+        b = 0
+        while b < len(batch):
+            e = b + 1
+            while e < len(batch) and batch[e].off0 == batch[b].off0:
+                e += 1
+            column = self._column(batch[b].off0)
+            groups, offs, masks, outs = [], [], [], []
+            for k in range(b, e):
+                sg = batch[k]
+                mask1 = _device_mask(sg.mask1, self.device)
+                for row, off0 in enumerate(self.my_rows):
+                    groups.append([(column[i], self.facet_configs[i].off1)
+                                   for i in self.local_idx
+                                   if self.facet_configs[i].off0 == off0])
+                    offs.append(sg.off1)
+                    masks.append(mask1)
+                    outs.append(views[k][slot, self.rank, row])
+            self.core.sum_finish_axis_grouped(groups, outs, axis=1, subgrid_off=offs, mask=masks)
+            self.launches += 1
+            b = e
+
     def _run_p2p(self, batches, xA, consumer, results):
-        """Strips go straight into the owners' symmetric buffers (NVLink stores from the
-        axis-1 kernel); one device-side barrier per batch."""
-        hdl, views, _ = self._symm_slots(xA)
-        for bi, batch in enumerate(batches):
-            slot = bi % 2
-            for b, sg in enumerate(batch):
-                # owner of this subgrid is rank b: write my strips into ITS slot, at my index
-                self._local_strips(sg, views[b][slot, self.rank])
-            hdl.barrier(channel=slot)
+        """Peer-memory exchange, software pipelined.
+
+        Per batch ``k`` the stream carries: axis-1 kernel of batch ``k`` (its finished lines
+        are scattered into the owners' slots by the TMA engine, over NVLink), ``signal(k)``,
+        ``wait(k - 1)``, axis-0 kernel of batch ``k - 1``.  The wait for batch ``k - 1`` thus
+        comes one whole axis-1 kernel after the signal: unless a rank lags by more than a batch
+        nobody ever blocks, and no SM runs a communication kernel.  A slot is rewritten four
+        batches later: by then every owner is known (through ``signal(k - 2)``, which follows
+        its axis-0 kernel of batch ``k - 4`` on its stream) to have consumed it.
+        """
+        _, views, _ = self._symm_slots(xA)
+        _, _, table, my_flags, status = self._symm_flags()
+        base = self._symm["seq"]
+        self._symm["seq"] = base + len(batches)
+
+        def finish(bi):
+            self.core.peer_wait(my_flags, self.world, base + bi + 1, status)
+            batch = batches[bi]
             if self.rank < len(batch):
                 idx = bi * self.world + self.rank
-                out = self._finish(batch[self.rank], views[self.rank][slot])
+                out = self._finish(batch[self.rank], views[self.rank][bi % self.N_SLOTS])
                 if consumer is not None:
                     consumer(idx, batch[self.rank], out)
                 else:
                     results[idx] = DeviceTask(out)
+
+        for bi, batch in enumerate(batches):
+            self._local_strips_batch_p2p(batch, views, bi % self.N_SLOTS)
+            self.core.peer_signal(table, self.world, self.rank, base + bi + 1, my_flags)
+            if bi >= 1:
+                finish(bi - 1)
+        finish(len(batches) - 1)
+        bad = int(status.item())
+        if bad:
+            raise RuntimeError(f"rank {self.rank}: rank {bad - 1} did not deliver its strips "
+                               "(peer wait timed out)")
         return results
 
 

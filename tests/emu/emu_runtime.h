@@ -100,13 +100,21 @@ struct HostCtx {
     inline void fence_async() const {}
     inline void bulk_commit() const {}
     inline void bulk_wait_read() const {}
+    inline void bulk_wait_all() const {}
     inline void tensor_store(const void* map, const void* smem_src, int c1, int c2, int c3) const;
+    inline void tensor_load(void* smem_dst, const void* map, int c1, int c2, uint64_t* bar) const;
 };
 
 }  // namespace swiftly
 namespace swiftly {
 struct TensorMap4;
 void emu_tensor_store(const TensorMap4* map, const double* src, int c1, int c2, int c3);
+void emu_tensor_load(const TensorMap4* map, double* dst, int c1, int c2);
+inline void HostCtx::tensor_load(void* smem_dst, const void* map, int c1, int c2,
+                                 uint64_t* bar) const {
+    emu_tensor_load((const TensorMap4*)map, (double*)smem_dst, c1, c2);
+    *bar += 1;
+}
 inline void HostCtx::tensor_store(const void* map, const void* smem_src, int c1, int c2,
                                   int c3) const {
     emu_tensor_store((const TensorMap4*)map, (const double*)smem_src, c1, c2, c3);

@@ -35,7 +35,7 @@ def emu_core_class():
             finally:
                 _lib.load = real_load
             if force_split:
-                lib.swiftly_b200_debug_force_split(self._plan, 1)
+                lib.swiftly_b200_debug_force_split(self._plan, int(force_split))
 
         def _check_tensor(self, t):
             assert not t.is_cuda

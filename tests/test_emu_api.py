@@ -51,3 +51,36 @@ def test_emu_forward_backward_vs_oracle_kernel_variants(sg_variant):
     """Every variant of the fused subgrid kernel (0: ping-pong + tokens + TMA tensor stores,
     1: round-1 kernel, 2: ping-pong without tokens, 5: ping-pong with direct stores)."""
     api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)
+
+
+@pytest.mark.parametrize("force_split", [1, 2])
+def test_emu_forward_split_k2_kernels(force_split):
+    """K2 through the split kernels that serve yN = 16384 on the GPU, forced at yN = 512:
+    1 = 2 x 256 (one thread group, E parked in the scratch), 2 = 4 x 128 (two thread groups on
+    the same TMA-staged, swizzled row)."""
+    import numpy
+
+    from oracle.swiftly_oracle import OracleCore, forward_reference_order
+    from ska_sdp_distributed_fourier_transform_b200 import FacetConfig, SubgridConfig, SwiftlyForward
+    from tests import parity_cases as pc
+
+    # (yB / yN = 0.5 like the BASELINE configs: well conditioned, see tests/test_gpu_parity.py)
+    W, N, yB, yN, xA, xM = 13.5625, 1024, 256, 512, 128, 256
+    cfg = make_config(W, N, yB, yN, xA, xM, force_split=force_split)
+    oracle = OracleCore(W, N, xM, yN)
+    rng = numpy.random.default_rng(force_split)
+    offs = [(0, 256), (256, -256), (-256, 0)]
+    facets = [pc.rand_c(rng, yB, yB), pc.rand_c(rng, yB, yB), pc.rand_c(rng, yB - 1, yB - 1)]
+    sgs = [SubgridConfig(128, -128, xA), SubgridConfig(128, 384, xA), SubgridConfig(-384, 0, xA)]
+    fwd = SwiftlyForward(cfg, [(FacetConfig(a, b, f.shape[0]), f) for (a, b), f in zip(offs, facets)])
+    got = [fwd.get_subgrid_task(sg).result() for sg in sgs]
+    # (the oracle's driver takes one facet size: run the odd-sized facet separately and add)
+    ref = forward_reference_order(oracle, facets[:2], offs[:2], [(s.off0, s.off1) for s in sgs], xA)
+    ref2 = forward_reference_order(oracle, facets[2:], offs[2:], [(s.off0, s.off1) for s in sgs], xA)
+    for a, b, c in zip(got, ref, ref2):
+        assert numpy.abs(a - (b + c)).max() <= 1e-12 * numpy.abs(b + c).max()
+    # only the facets whose rows are whole 128-byte chunks: staged by swizzled tensor loads
+    fwd = SwiftlyForward(cfg, [(FacetConfig(a, b, yB), f) for (a, b), f in zip(offs[:2], facets)])
+    for sg, b in zip(sgs, ref):
+        a = fwd.get_subgrid_task(sg).result()
+        assert numpy.abs(a - b).max() <= 1e-12 * numpy.abs(b).max()
