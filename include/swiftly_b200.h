@@ -184,6 +184,18 @@ int swiftly_b200_peer_wait(const swiftly_b200* plan, const void* my_flags, int n
 int swiftly_b200_extract_columns(const swiftly_b200* plan, int n_facets,
                                  const swiftly_b200_lines* bf_f, const swiftly_b200_lines* out,
                                  int64_t subgrid_off0, const int64_t* facet_off1, void* stream);
+/* The pair the fused forward driver uses between stage 1 and K2: prepare_facet whose output
+ * LINES are pre-multiplied by the Fb window of the other axis (line l by Fb_c[l], the factor
+ * prepare_facet(axis 1) would apply to sample l), and extract_columns that takes such rows and
+ * skips its own window multiply.  Together they equal prepare_facet + extract_columns
+ * (core.py:189-222 applied along axis 0, then api_helper.py:200-210). */
+int swiftly_b200_prepare_facet_windowed(const swiftly_b200* plan, const swiftly_b200_lines* in,
+                                        const swiftly_b200_lines* out, int64_t facet_off,
+                                        void* stream);
+int swiftly_b200_extract_columns_windowed(const swiftly_b200* plan, int n_facets,
+                                          const swiftly_b200_lines* bf_f,
+                                          const swiftly_b200_lines* out, int64_t subgrid_off0,
+                                          const int64_t* facet_off1, void* stream);
 /* ---- fused backward path (device memory only) --------------------------------------- */
 /* One subgrid into the column accumulators of n_facets (<= 64) facets in ONE launch: per
  * facet `extract_from_subgrid(block, facet_off1, axis=1)` followed by `accumulate_column` =

@@ -64,6 +64,7 @@ SYMBOLS = {
     "swiftly_b200_build_info": (ctypes.c_char_p, []),
     "swiftly_b200_contribution_size": (ctypes.c_int64, [_PLAN]),
     "swiftly_b200_prepare_facet": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
+    "swiftly_b200_prepare_facet_windowed": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_extract_from_facet": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_add_to_subgrid": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_finish_subgrid": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
@@ -79,6 +80,7 @@ SYMBOLS = {
     "swiftly_b200_peer_signal": (ctypes.c_int, [_PLAN, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_peer_wait": (ctypes.c_int, [_PLAN, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "swiftly_b200_extract_columns": (ctypes.c_int, [_PLAN, ctypes.c_int, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]),
+    "swiftly_b200_extract_columns_windowed": (ctypes.c_int, [_PLAN, ctypes.c_int, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]),
     "swiftly_b200_subgrid_to_facets": (ctypes.c_int, [_PLAN, ctypes.c_int, _LINES_P, _LINES_P, ctypes.POINTER(ctypes.c_int64), ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_fold_column": (ctypes.c_int, [_PLAN, ctypes.c_int, _LINES_P, _LINES_P, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_sum_finish_axis_supported": (ctypes.c_int, [_PLAN]),

@@ -390,7 +390,12 @@ class SwiftlyForward:
             uploads = _upload_iter([data for _, data in self.facet_tasks], self.device)
             for idx, ((cfg, _), facet) in enumerate(zip(self.facet_tasks, uploads)):
                 buf = None if self._bf_f_buffers is None else self._bf_f_buffers[idx]
-                out.append(self.core.prepare_facet(facet, cfg.off0, axis=0, out=buf))
+                if self._fused:
+                    # pre-windowed along axis 1 (the K2 kernel then skips its Fb multiply)
+                    out.append(self.core.prepare_facet(facet, cfg.off0, axis=0, out=buf,
+                                                       window_lines=True))
+                else:
+                    out.append(self.core.prepare_facet(facet, cfg.off0, axis=0, out=buf))
                 del facet
             # facets are dead from here on: drop the references held by the task list
             self.facet_tasks = [(cfg, None) for cfg, _ in self.facet_tasks]
@@ -408,7 +413,8 @@ class SwiftlyForward:
                 _, reuse = self.lru.data.popitem(last=False)
             if self._fused:
                 cached = self.core.extract_columns(
-                    BF_Fs, off0, [cfg.off1 for cfg, _ in self.facet_tasks], outs=reuse)
+                    BF_Fs, off0, [cfg.off1 for cfg, _ in self.facet_tasks], outs=reuse,
+                    prewindowed=True)
             else:
                 cached = [extract_column(self.core, BF_F, off0, cfg.off1)
                           for (cfg, _), BF_F in zip(self.facet_tasks, BF_Fs)]

@@ -217,19 +217,23 @@ class ForwardBenchRunner:
         sg = self.sg_cfgs[len(self.sg_cfgs) // 2 + 3]
         out = {}
         t1 = self._time(lambda: core.prepare_facet(
-            self.facet_views[idx0], fcs[idx0].off0, axis=0, out=self.bf_views[idx0]), 3)
+            self.facet_views[idx0], fcs[idx0].off0, axis=0, out=self.bf_views[idx0],
+            window_lines=True), 3)
         out["prepare_facet_axis0"] = (t1, 16.0 * (yB * yB + yN * yB), F)
         # make the row's BF_F valid for the following kernels
         for i in row_members:
-            core.prepare_facet(self.facet_views[i], fcs[i].off0, axis=0, out=self.bf_views[i])
+            core.prepare_facet(self.facet_views[i], fcs[i].off0, axis=0, out=self.bf_views[i],
+                               window_lines=True)
         # stage 2 exactly as the step launches it: all local facets of a column in one launch
         for i in self.local_idx:
-            core.prepare_facet(self.facet_views[i], fcs[i].off0, axis=0, out=self.bf_views[i])
+            core.prepare_facet(self.facet_views[i], fcs[i].off0, axis=0, out=self.bf_views[i],
+                               window_lines=True)
         nmbf_all = [torch.empty((m, yN), dtype=torch.complex128, device=dev)
                     for _ in self.local_idx]
         bfs = [self.bf_views[i] for i in self.local_idx]
         off1s = [fcs[i].off1 for i in self.local_idx]
-        t2 = self._time(lambda: core.extract_columns(bfs, sg.off0, off1s, outs=nmbf_all), 3)
+        t2 = self._time(lambda: core.extract_columns(bfs, sg.off0, off1s, outs=nmbf_all,
+                                                     prewindowed=True), 3)
         out["extract_columns (Fb.FFT.extract, K2; all local facets of a column)"] = (
             t2, 16.0 * (m * yB + m * yN) * F, ncols)
         nmbf = dict(zip(self.local_idx, nmbf_all))

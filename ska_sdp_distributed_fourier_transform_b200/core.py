@@ -246,9 +246,16 @@ class SwiftlyCoreB200:
         return out
 
     # ------------------------------------------------------------------ facet -> subgrid
-    def prepare_facet(self, facet, facet_off, axis, out=None):
-        """Prepare facet for extracting subgrid contributions (core.py:189-222)."""
-        return self._run("swiftly_b200_prepare_facet", facet, self.yN_size, axis, out, facet_off)
+    def prepare_facet(self, facet, facet_off, axis, out=None, window_lines=False):
+        """Prepare facet for extracting subgrid contributions (core.py:189-222).
+
+        ``window_lines`` (fused forward path only, not part of the reference interface): every
+        output line ``l`` (index along the OTHER axis) is additionally multiplied by the facet
+        window ``Fb`` at ``l`` -- the factor ``prepare_facet`` along the other axis would apply
+        -- so that :meth:`extract_columns` (``prewindowed=True``) need not fetch it per sample.
+        """
+        fn = "swiftly_b200_prepare_facet_windowed" if window_lines else "swiftly_b200_prepare_facet"
+        return self._run(fn, facet, self.yN_size, axis, out, facet_off)
 
     def extract_from_facet(self, prep_facet, subgrid_off, axis, out=None):
         """Extract the facet contribution to a subgrid (core.py:224-253)."""
@@ -371,8 +378,11 @@ class SwiftlyCoreB200:
         _lib.check(self._lib, rc)
         return out
 
-    def extract_columns(self, BF_Fs, subgrid_off0, facet_off1s, outs=None):
-        """``extract_column`` for a list of facets in ONE kernel launch (<= 64 per launch)."""
+    def extract_columns(self, BF_Fs, subgrid_off0, facet_off1s, outs=None, prewindowed=False):
+        """``extract_column`` for a list of facets in ONE kernel launch (<= 64 per launch).
+
+        ``prewindowed``: the ``BF_Fs`` were made with ``prepare_facet(..., window_lines=True)``.
+        """
         shape = (self.xM_yN_size, self.yN_size)
         BF_Fs = list(BF_Fs)
         if outs is None:
@@ -397,9 +407,10 @@ class SwiftlyCoreB200:
                 din[k] = self._describe(b, 1)
                 dout[k] = self._describe(o, 1)
                 offs[k] = int(facet_off1s[i])
-            rc = self._lib.swiftly_b200_extract_columns(
-                self._plan, len(chunk), din, dout, int(subgrid_off0), offs,
-                self._stream(BF_Fs[lo]))
+            entry = (self._lib.swiftly_b200_extract_columns_windowed if prewindowed
+                     else self._lib.swiftly_b200_extract_columns)
+            rc = entry(self._plan, len(chunk), din, dout, int(subgrid_off0), offs,
+                       self._stream(BF_Fs[lo]))
             _lib.check(self._lib, rc)
         return outs
 

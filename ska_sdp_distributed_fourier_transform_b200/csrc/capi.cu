@@ -321,11 +321,19 @@ bool lines_adjacent(const Lines& g) {
     Lines g = make_lines(sin, sout, in->n_lines);
 
 // ------------------------------------------------------------------ facet -> subgrid
-extern "C" int swiftly_b200_prepare_facet(const swiftly_b200* h, const swiftly_b200_lines* in,
-                                          const swiftly_b200_lines* out, int64_t facet_off,
-                                          void* stream) {
+static int prepare_facet_impl(const swiftly_b200* h, const swiftly_b200_lines* in,
+                              const swiftly_b200_lines* out, int64_t facet_off, bool windowed,
+                              void* stream) {
     SW_PROLOGUE("prepare_facet", -1, h ? h->yN : -1, false)
     const int64_t yN = h->yN, fs = in->size;
+    // windowed: line l of the output is additionally multiplied by Fb_c[l], the window the
+    // NEXT prepare_facet (along the other axis) would apply to sample l of its lines
+    const double* lw = nullptr;
+    if (windowed) {
+        if (g.n_lines > yN - 1)
+            return einval("prepare_facet_windowed: more lines than the window is long");
+        lw = h->d_Fb + ((yN - 1) / 2 - g.n_lines / 2);
+    }
     // extract_mid(Fb, fs) needs fs <= len(Fb) = yN - 1 (core.py:213-215)
     if (fs > yN - 1) return einval("prepare_facet: facet size must be at most yN_size - 1");
     // Strided axis with many adjacent lines: two-pass transform with coalesced column runs.
@@ -335,31 +343,47 @@ extern "C" int swiftly_b200_prepare_facet(const swiftly_b200* h, const swiftly_b
         while (((int64_t)1 << lg) < yN) ++lg;
         const int n1 = 1 << ((lg + 1) / 2), n2 = (int)(yN / n1);
         const cplx* twf = twiddles_full(h, (int)yN);
-        cplx* scratch = split_scratch(h, s, (size_t)yN * (size_t)g.n_lines);
+        // Column tiles bound the scratch T (yN x tile samples) to 2 GiB.  Smaller tiles that
+        // would keep T in the 126 MB L2 between the passes were measured and LOSE: 2.35 ms per
+        // N=65536 facet with 64 MiB tiles, 2.20 ms with 128 MiB, 2.00 ms with one tile (the
+        // short launches pay more in tails than the L2 hits save).
+        int64_t tile = ((int64_t)128 << 20) / yN;  // 2 GiB of complex128
+        tile = tile / 16 * 16;
+        if (tile < 16) tile = 16;
+        if (h->sg_variant == 9) tile = ((int64_t)4 << 20) / yN;  // debug hook: 64 MiB tiles
+        if (h->sg_variant == 10) tile = 32;  // tests: several tiles, ragged last one
+        if (tile > g.n_lines) tile = g.n_lines;
+        cplx* scratch = split_scratch(h, s, (size_t)yN * (size_t)tile);
         if (!twf || !scratch) return SWIFTLY_B200_ECUDA;
-        PrepareFacetPassAOp a;
-        a.g = g;
-        a.g.out = scratch;
-        a.g.n_lines = (int64_t)n2 * g.n_lines;
-        a.fb = h->d_Fb + ((yN - 1) / 2 - fs / 2);
-        a.twf = twf;
-        a.n = (int)yN;
-        a.n1 = n1;
-        a.n2 = n2;
-        a.fs = (int)fs;
-        a.shift_in = (int)pmod(fs / 2 - facet_off, yN);
-        a.ncols = (int)g.n_lines;
-        SW_TRY(run_prepare_facet_pass_a(h, a, s));
-        PrepareFacetPassBOp b;
-        b.g = g;
-        b.g.in = scratch;
-        b.g.n_lines = (int64_t)n1 * g.n_lines;
-        b.n = (int)yN;
-        b.n1 = n1;
-        b.n2 = n2;
-        b.ncols = (int)g.n_lines;
-        b.scale = 1.0 / (double)yN;
-        SW_TRY(run_prepare_facet_pass_b(h, b, s));
+        for (int64_t c0 = 0; c0 < g.n_lines; c0 += tile) {
+            const int64_t nc = g.n_lines - c0 < tile ? g.n_lines - c0 : tile;
+            PrepareFacetPassAOp a;
+            a.g = g;
+            a.g.in = g.in + c0;
+            a.g.out = scratch;
+            a.g.n_lines = (int64_t)n2 * nc;
+            a.fb = h->d_Fb + ((yN - 1) / 2 - fs / 2);
+            a.twf = twf;
+            a.n = (int)yN;
+            a.n1 = n1;
+            a.n2 = n2;
+            a.fs = (int)fs;
+            a.shift_in = (int)pmod(fs / 2 - facet_off, yN);
+            a.ncols = (int)nc;
+            SW_TRY(run_prepare_facet_pass_a(h, a, s));
+            PrepareFacetPassBOp b;
+            b.g = g;
+            b.g.in = scratch;
+            b.g.out = g.out + c0;
+            b.g.n_lines = (int64_t)n1 * nc;
+            b.n = (int)yN;
+            b.n1 = n1;
+            b.n2 = n2;
+            b.ncols = (int)nc;
+            b.scale = 1.0 / (double)yN;
+            b.lw = lw ? lw + c0 : nullptr;
+            SW_TRY(run_prepare_facet_pass_b(h, b, s));
+        }
         return stage_out(sout, s);
     }
     PrepareFacetOp op;
@@ -373,8 +397,24 @@ extern "C" int swiftly_b200_prepare_facet(const swiftly_b200* h, const swiftly_b
     op.rm_m = 0;
     op.rm_s_m = op.rm_base = 0;
     op.rm_mod = 1;
+    op.lw = lw;
     SW_TRY(run_prepare_facet(h, op, lines_adjacent(g), s));
     return stage_out(sout, s);
+}
+
+extern "C" int swiftly_b200_prepare_facet(const swiftly_b200* h, const swiftly_b200_lines* in,
+                                          const swiftly_b200_lines* out, int64_t facet_off,
+                                          void* stream) {
+    return prepare_facet_impl(h, in, out, facet_off, false, stream);
+}
+
+// prepare_facet whose output lines are pre-multiplied by the Fb window of the other axis
+// (fused forward path: stage 1 hands K2 rows that need no window fetch per sample)
+extern "C" int swiftly_b200_prepare_facet_windowed(const swiftly_b200* h,
+                                                   const swiftly_b200_lines* in,
+                                                   const swiftly_b200_lines* out,
+                                                   int64_t facet_off, void* stream) {
+    return prepare_facet_impl(h, in, out, facet_off, true, stream);
 }
 
 extern "C" int swiftly_b200_extract_from_facet(const swiftly_b200* h,

@@ -39,6 +39,7 @@ extern "C" int swiftly_b200_extract_column(const swiftly_b200* h, const swiftly_
     op.rm_s_m = (int)pmod(sc, m);
     op.rm_base = (int)pmod(yN / 2 - m / 2 + sc, yN);
     op.rm_mod = (int)yN;
+    op.lw = nullptr;
     return run_prepare_facet(h, op, false, (cudaStream_t)stream);
 }
 
@@ -256,11 +257,10 @@ extern "C" int swiftly_b200_sum_finish_axis(const swiftly_b200* h,
 }
 
 // extract_column for several facets in one launch (same subgrid_off0; per-facet off1).
-extern "C" int swiftly_b200_extract_columns(const swiftly_b200* h, int n_facets,
-                                            const swiftly_b200_lines* bf_f,
-                                            const swiftly_b200_lines* out,
-                                            int64_t subgrid_off0, const int64_t* facet_off1,
-                                            void* stream) {
+static int extract_columns_impl(const swiftly_b200* h, int n_facets,
+                                const swiftly_b200_lines* bf_f, const swiftly_b200_lines* out,
+                                int64_t subgrid_off0, const int64_t* facet_off1, int prewindowed,
+                                void* stream) {
     if (!h || !bf_f || !out || !facet_off1) return einval("extract_columns: NULL argument");
     if (n_facets < 1 || n_facets > SW_MAX_COLUMN_FACETS)
         return einval("extract_columns: between 1 and " + std::to_string(SW_MAX_COLUMN_FACETS) +
@@ -293,13 +293,30 @@ extern "C" int swiftly_b200_extract_columns(const swiftly_b200* h, int n_facets,
     op.g.out = nullptr;
     op.g.in_ls = op.g.in_es = op.g.out_ls = op.g.out_es = 0;
     op.g.n_lines = (int64_t)n_facets * m;
-    op.fb = h->d_Fb;
+    op.fb = prewindowed ? nullptr : h->d_Fb;
     op.n = (int)yN;
     op.lines_per = (int)m;
     op.scale = 1.0 / (double)yN;
     op.rm_s_m = (int)pmod(sc, m);
     op.rm_base = (int)pmod(yN / 2 - m / 2 + sc, yN);
     return run_extract_columns(h, op, false, (cudaStream_t)stream);
+}
+
+extern "C" int swiftly_b200_extract_columns(const swiftly_b200* h, int n_facets,
+                                            const swiftly_b200_lines* bf_f,
+                                            const swiftly_b200_lines* out,
+                                            int64_t subgrid_off0, const int64_t* facet_off1,
+                                            void* stream) {
+    return extract_columns_impl(h, n_facets, bf_f, out, subgrid_off0, facet_off1, 0, stream);
+}
+
+// the rows of bf_f come from swiftly_b200_prepare_facet_windowed: no Fb multiply here
+extern "C" int swiftly_b200_extract_columns_windowed(const swiftly_b200* h, int n_facets,
+                                                     const swiftly_b200_lines* bf_f,
+                                                     const swiftly_b200_lines* out,
+                                                     int64_t subgrid_off0,
+                                                     const int64_t* facet_off1, void* stream) {
+    return extract_columns_impl(h, n_facets, bf_f, out, subgrid_off0, facet_off1, 1, stream);
 }
 
 // ---------------------------------------------------------------------- fused backward path

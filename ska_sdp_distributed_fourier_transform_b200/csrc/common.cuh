@@ -11,6 +11,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <type_traits>
 
 #if defined(SWIFTLY_EMU)
 #include "emu_runtime.h"
@@ -122,6 +123,7 @@ struct alignas(64) TensorMap4 {
 struct DeviceCtx {
     int tid, bid, nblocks;
     char* smem;
+    const void* tmaps;  // the kernel's tensor maps (a __grid_constant__ parameter) or null
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     // named barrier over `count` threads (a multiple of 32; whole warps), id 1..15
     __device__ __forceinline__ void group_sync(int id, int count) const {
@@ -217,13 +219,30 @@ struct MinBlocks {
 };
 
 template <class Body>
-__global__ void __launch_bounds__(Body::THREADS, MinBlocks<Body>::V)
-    kernel_entry(const __grid_constant__ Body body) {
+__global__ void __launch_bounds__(Body::THREADS, MinBlocks<Body>::V) kernel_entry(const Body body) {
     DeviceCtx ctx;
     ctx.tid = threadIdx.x;
     ctx.bid = blockIdx.x;
     ctx.nblocks = gridDim.x;
     ctx.smem = swiftly_dyn_smem;
+    ctx.tmaps = nullptr;
+    body(ctx);
+}
+
+// Kernels that use the TMA engine with tensor maps take the descriptors as a SEPARATE
+// __grid_constant__ parameter (the TMA instructions need the descriptor's address in the
+// parameter space); the body itself stays an ordinary by-value parameter -- measured: making
+// the whole body __grid_constant__ changes code generation of the memory-bound line kernels
+// for the worse (fewer registers, loads hoisted less far; prepare_facet 2.39 vs 2.02 ms).
+template <class Body>
+__global__ void __launch_bounds__(Body::THREADS, MinBlocks<Body>::V)
+    kernel_entry_maps(const Body body, const __grid_constant__ typename Body::Maps maps) {
+    DeviceCtx ctx;
+    ctx.tid = threadIdx.x;
+    ctx.bid = blockIdx.x;
+    ctx.nblocks = gridDim.x;
+    ctx.smem = swiftly_dyn_smem;
+    ctx.tmaps = &maps;
     body(ctx);
 }
 
@@ -238,6 +257,20 @@ inline cudaError_t launch_body(const Body& body, int grid, size_t smem_bytes, cu
         if (e != cudaSuccess) return e;
     }
     kernel_entry<Body><<<grid, Body::THREADS, smem_bytes, stream>>>(body);
+    return cudaGetLastError();
+}
+
+template <class Body>
+inline cudaError_t launch_body_maps(const Body& body, const typename Body::Maps& maps, int grid,
+                                    size_t smem_bytes, cudaStream_t stream) {
+    if (grid <= 0) return cudaSuccess;
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel_entry_maps<Body>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    kernel_entry_maps<Body><<<grid, Body::THREADS, smem_bytes, stream>>>(body, maps);
     return cudaGetLastError();
 }
 #endif

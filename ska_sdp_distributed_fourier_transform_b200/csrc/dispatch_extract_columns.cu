@@ -12,6 +12,7 @@ static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op,
                               cudaStream_t s) {
     typedef ExtractColumnsTmaKernel<H, SPLIT> K;
     K k;
+    static thread_local typename K::Maps maps;
     k.op = op;
     k.tw = twiddles(h, H);
     k.tw2 = SPLIT ? twiddles_full(h, 2 * H) : nullptr;
@@ -33,7 +34,7 @@ static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op,
         const int boxes = (max_fs / 8 + k.box_chunks - 1) / k.box_chunks;
         k.in_cap = boxes * k.box_chunks * 8;
         for (int f = 0; f < n_facets && k.swizzled; ++f)
-            if (!make_row_map(&k.in_map[f], op.fac[f].in, op.fac[f].in_ls, op.n, op.fac[f].fs,
+            if (!make_row_map(&maps.in_map[f], op.fac[f].in, op.fac[f].in_ls, op.n, op.fac[f].fs,
                               k.box_chunks))
                 k.swizzled = 0;
         if (!k.swizzled) k.in_cap = (max_fs + 1) & ~1;
@@ -53,7 +54,7 @@ static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op,
         k.scratch = split_scratch(h, s, (size_t)blocks * H);
         if (!k.scratch) return SWIFTLY_B200_ECUDA;
     }
-    cudaError_t e = launch_body(k, (int)blocks, smem, s);
+    cudaError_t e = launch_body_maps(k, maps, (int)blocks, smem, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "extract_columns (TMA) kernel launch");
 }
 
@@ -63,6 +64,7 @@ static int launch_extract_tma4(const swiftly_b200* h, const ExtractColumnsOp& op
                                cudaStream_t s) {
     typedef ExtractColumnsTma4Kernel<Q> K;
     K k;
+    static thread_local typename K::Maps maps;
     k.op = op;
     k.tw = twiddles(h, Q);
     k.twf = twiddles_full(h, 4 * Q);
@@ -82,7 +84,7 @@ static int launch_extract_tma4(const swiftly_b200* h, const ExtractColumnsOp& op
         const int boxes = (max_fs / 8 + k.box_chunks - 1) / k.box_chunks;
         k.in_cap = boxes * k.box_chunks * 8;
         for (int f = 0; f < n_facets && k.swizzled; ++f)
-            if (!make_row_map(&k.in_map[f], op.fac[f].in, op.fac[f].in_ls, op.n, op.fac[f].fs,
+            if (!make_row_map(&maps.in_map[f], op.fac[f].in, op.fac[f].in_ls, op.n, op.fac[f].fs,
                               k.box_chunks))
                 k.swizzled = 0;
         if (!k.swizzled) k.in_cap = (max_fs + 1) & ~1;
@@ -100,7 +102,7 @@ static int launch_extract_tma4(const swiftly_b200* h, const ExtractColumnsOp& op
     if (blocks > op.g.n_lines) blocks = op.g.n_lines;
     k.scratch = split_scratch(h, s, (size_t)blocks * 4 * Q);
     if (!k.scratch) return SWIFTLY_B200_ECUDA;
-    cudaError_t e = launch_body(k, (int)blocks, smem, s);
+    cudaError_t e = launch_body_maps(k, maps, (int)blocks, smem, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK
                             : cuda_fail(e, "extract_columns (TMA, 4-way split) kernel launch");
 }

@@ -35,7 +35,9 @@ static int launch_sg_axis_l(const swiftly_b200* h, const SubgridAxisArgs& a, cud
 // ping-pong variant: two thread groups (two lines) per CTA, LSU token between them
 template <int M, int XM, bool TOKENS>
 static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cudaStream_t s) {
-    SubgridAxisKernelPP<M, XM, TOKENS> k;
+    typedef SubgridAxisKernelPP<M, XM, TOKENS> K;
+    K k;
+    static thread_local typename K::Maps maps;
     for (int i = 0; i < SW_MAX_SOURCES; ++i) k.src[i] = a.src[i];
     k.n_slots = a.n_slots;
     k.n_groups = a.n_groups;
@@ -63,6 +65,7 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
     k.tma_box = a.sz < 256 ? a.sz : 256;
     k.tma_slot_line = k.tma_slot_elem = k.tma_slot_group = 1;
     k.tma_per_group = a.out_g[0] != nullptr ? 1 : 0;
+    k.pf_mode = h->sg_variant == 11 ? 1 : (h->sg_variant == 12 ? 2 : 0);
     // (the last box may be partial: the engine still reads a whole box from shared memory)
     const size_t staged = (size_t)((a.sz + k.tma_box - 1) / (k.tma_box > 0 ? k.tma_box : 1)) *
                           (size_t)k.tma_box * sizeof(cplx);
@@ -73,10 +76,10 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
         if (k.tma_per_group) {
             // (the slots depend on the strides only, which all groups share)
             for (int g = 0; g < a.n_groups && ok; ++g)
-                ok = make_out_map(&k.out_map[g], a.out_g[g], a.out_ls, a.out_es, 0, a.n_lines,
+                ok = make_out_map(&maps.out_map[g], a.out_g[g], a.out_ls, a.out_es, 0, a.n_lines,
                                   a.sz, 1, k.tma_box, slot);
         } else {
-            ok = make_out_map(&k.out_map[0], a.out, a.out_ls, a.out_es, a.out_gs, a.n_lines,
+            ok = make_out_map(&maps.out_map[0], a.out, a.out_ls, a.out_es, a.out_gs, a.n_lines,
                               a.sz, a.n_groups, k.tma_box, slot);
         }
         if (ok) {
@@ -89,8 +92,8 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
     // persistent: one CTA per SM, every CTA walks over line pairs
     int64_t pairs = ((a.n_lines + 1) / 2) * a.n_groups;
     int grid = (int)(pairs < 148 ? pairs : 148);
-    cudaError_t e = launch_body(k, grid, k.SMEM, s);
-    return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "subgrid axis (ping-pong) kernel launch");
+    cudaError_t e = launch_body_maps(k, maps, grid, k.SMEM, s);
+    return e == cudaSuccess ? SWIFTLY_B200_OK : cuda_fail(e, "subgrid axis (two-group) kernel launch");
 }
 
 template <int M, int XM>
@@ -111,11 +114,12 @@ static int launch_sg_axis(const swiftly_b200* h, const SubgridAxisArgs& a, cudaS
     for (int i = 0; i < SW_MAX_SOURCES && adjacent; ++i)
         if (a.src[i].base && a.src[i].ls != 1) adjacent = false;
     if constexpr (PingPongFits<M, XM>::V) {
-        // sg_variant (debug hook): 0 = ping-pong with tokens, 1 = round-1 kernel,
-        // 2 = ping-pong layout without tokens
+        // sg_variant (debug hook): 0 = two-group kernel (default), 1 = round-1 kernel,
+        // 2 = two-group kernel WITH the LSU token (measured slower: a single group cannot
+        // saturate either pipe alone, see subgrid_pp.cuh), 5 = two-group, direct stores
         if (!adjacent && h->sg_variant != 1)
-            return h->sg_variant == 2 ? launch_sg_axis_pp<M, XM, false>(h, a, s)
-                                      : launch_sg_axis_pp<M, XM, true>(h, a, s);
+            return h->sg_variant == 2 ? launch_sg_axis_pp<M, XM, true>(h, a, s)
+                                      : launch_sg_axis_pp<M, XM, false>(h, a, s);
     }
     // 2 lines need 2 x (acc + work) of shared memory: only the pairs that fit
     if constexpr (2 * ((size_t)(XM + 4) * sizeof(cplx) + (size_t)(XM + XM / 16 + 40) * 8) <=

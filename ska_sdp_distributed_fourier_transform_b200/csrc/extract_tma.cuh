@@ -43,7 +43,10 @@ struct ExtractColumnsTmaKernel {
     // bank conflict on a linear buffer, conflict free on the swizzled one
     int swizzled;
     int box_chunks;  // 128-byte chunks per tensor load
-    TensorMap4 in_map[SW_MAX_COLUMN_FACETS];
+    // tensor maps travel as a separate __grid_constant__ kernel parameter (ctx.tmaps)
+    struct Maps {
+        TensorMap4 in_map[SW_MAX_COLUMN_FACETS];
+    };
 
     // first-pass loads must be done before the staging buffer is refilled: the refill is issued
     // by thread 0 right after the first barrier that follows them
@@ -76,7 +79,8 @@ struct ExtractColumnsTmaKernel {
             // (a box that sticks out of the row is zero filled and still counts in full)
             ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
             for (int c0 = 0; c0 < chunks; c0 += box_chunks)
-                ctx.tensor_load((char*)in + (size_t)c0 * 128, &in_map[f], c0, (int)row, bar);
+                ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
+                                (int)row, bar);
             return;
         }
         const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
@@ -109,7 +113,7 @@ struct ExtractColumnsTmaKernel {
             const int l = (int)(line - (int64_t)f * op.lines_per);
             const ColumnFacet& F = op.fac[f];
             const int shift_in = F.shift_in, fs = F.fs;
-            const double* fb = op.fb + F.fb_off;
+            const double* fb = op.fb ? op.fb + F.fb_off : nullptr;
             cplx* o = F.out + (int64_t)l * F.out_ls;
             const double scale = op.scale;
             const bool swz = swizzled != 0;
@@ -118,7 +122,7 @@ struct ExtractColumnsTmaKernel {
                 int k = wrap_add(q, shift_in, n);
                 if (k >= fs) return mk(0.0, 0.0);
                 const int ks = swz ? ((k & ~7) | ((k ^ (k >> 3)) & 7)) : k;
-                return cscale(in[ks], ldg_d(fb + k));
+                return fb ? cscale(in[ks], ldg_d(fb + k)) : in[ks];
             };
             auto put = [&](int p, cplx v) {
                 int pc = wrap_add(p, n / 2, n);
@@ -137,9 +141,25 @@ struct ExtractColumnsTmaKernel {
                 ctx.sync();
                 {
                     auto ld = [&](int q) { return sample(2 * q + 1); };
-                    auto st = [&](int k, cplx od) {
-                        cplx w = ldg_c(tw2 + k);
+                    // w^k for the thread's outputs k = j0 + it * T + r * NS by recurrence: one
+                    // table load per thread, then multiplications by the two step factors
+                    // w^T and w^NS (loading every w^k exposed an L2 round trip per output)
+                    typedef LastPass<H> LP;
+                    auto unit = [&](int t) {  // exp(DIR 2 pi i t / 2H), 0 <= t < 2H
+                        const bool neg = t >= H;
+                        cplx w = ldg_c(tw2 + (neg ? t - H : t));
                         if (DIR > 0) w.y = -w.y;
+                        return neg ? mk(-w.x, -w.y) : w;
+                    };
+                    const cplx step_it = unit(T), step_r = unit(LP::NS % (2 * H));
+                    cplx w_it = mk(1.0, 0.0), w = mk(1.0, 0.0);
+                    auto st = [&](int k, cplx od, int it, int r) {
+                        if (r == 0) {
+                            w_it = it == 0 ? unit(k) : cmul(w_it, step_it);
+                            w = w_it;
+                        } else {
+                            w = cmul(w, step_r);
+                        }
                         cplx e = stash[k];
                         cplx wo = cmul(od, w);
                         put(k, cadd(e, wo));
@@ -191,7 +211,9 @@ struct ExtractColumnsTma4Kernel {
     int in_cap;
     int swizzled;
     int box_chunks;
-    TensorMap4 in_map[SW_MAX_COLUMN_FACETS];
+    struct Maps {
+        TensorMap4 in_map[SW_MAX_COLUMN_FACETS];
+    };
 
     SW_HD cplx root(int t) const {  // exp(DIR 2 pi i t / N), 0 <= t < N
         const bool neg = t >= N / 2;
@@ -211,7 +233,8 @@ struct ExtractColumnsTma4Kernel {
             const int boxes = (chunks + box_chunks - 1) / box_chunks;
             ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
             for (int c0 = 0; c0 < chunks; c0 += box_chunks)
-                ctx.tensor_load((char*)in + (size_t)c0 * 128, &in_map[f], c0, (int)row, bar);
+                ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
+                                (int)row, bar);
             return;
         }
         const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
@@ -273,7 +296,7 @@ struct ExtractColumnsTma4Kernel {
             const int l = (int)(line - (int64_t)f * op.lines_per);
             const ColumnFacet& F = op.fac[f];
             const int shift_in = F.shift_in, fs = F.fs;
-            const double* fb = op.fb + F.fb_off;
+            const double* fb = op.fb ? op.fb + F.fb_off : nullptr;
             cplx* o = F.out + (int64_t)l * F.out_ls;
             const double scale = op.scale;
             const bool swz = swizzled != 0;
@@ -281,7 +304,7 @@ struct ExtractColumnsTma4Kernel {
                 int k = wrap_add(q, shift_in, n);
                 if (k >= fs) return mk(0.0, 0.0);
                 const int ks = swz ? ((k & ~7) | ((k ^ (k >> 3)) & 7)) : k;
-                return cscale(in[ks], ldg_d(fb + k));
+                return fb ? cscale(in[ks], ldg_d(fb + k)) : in[ks];
             };
             ctx.tx_wait(bar, parity);
             parity ^= 1;
@@ -291,21 +314,45 @@ struct ExtractColumnsTma4Kernel {
                 const int q4 = 2 * grp + qi;
                 cplx* sq = stash + (size_t)q4 * Q;
                 auto ld = [&](int j) { return sample(4 * j + q4); };
-                auto st = [&](int k, cplx v) { sq[k] = q4 ? cmul(v, root(q4 * k)) : v; };
+                // t_q[k] = w^(q k) E_q[k]; w^(q k) for the thread's outputs k = j0 + it * T +
+                // r * NS by recurrence: one table load, then multiplications by w^(q T), w^(q NS)
+                typedef LastPass<Q> LP;
+                const cplx step_it = root((q4 * TG) % N), step_r = root((q4 * LP::NS) % N);
+                cplx w_it = mk(1.0, 0.0), w = mk(1.0, 0.0);
+                auto st = [&](int k, cplx v, int it, int r) {
+                    if (r == 0) {
+                        w_it = it == 0 ? root((q4 * k) % N) : cmul(w_it, step_it);
+                        w = w_it;
+                    } else {
+                        w = cmul(w, step_r);
+                    }
+                    sq[k] = q4 ? cmul(v, w) : v;
+                };
                 gs.pending = (qi == 1);
                 line_fft<Q, DIR>(tg, sm, tw, ld, st, gs);
                 gs();  // the group's exchange buffer is reused by its next sub-transform
             }
             ctx.sync();  // all four t_q are in the scratch
-            for (int k = ctx.tid; k < Q; k += THREADS) {
-                cplx t[4];
+            // (four k per trip: sixteen independent scratch loads in flight per thread)
+            for (int k0 = ctx.tid; k0 < Q; k0 += 4 * THREADS) {
+                cplx t[4][4];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) t[q4] = stash[(size_t)q4 * Q + k];
-                Radix<4, DIR>::run(t);
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    int pc = wrap_add(k + Q * s4, n / 2, n);
-                    st_stream(o + pc, cscale(t[s4], scale));
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int k = k0 + i * THREADS;
+                        t[i][q4] = k < Q ? stash[(size_t)q4 * Q + k] : mk(0.0, 0.0);
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = k0 + i * THREADS;
+                    if (k >= Q) break;
+                    Radix<4, DIR>::run(t[i]);
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        int pc = wrap_add(k + Q * s4, n / 2, n);
+                        st_stream(o + pc, cscale(t[i][s4], scale));
+                    }
                 }
             }
             ctx.sync();  // scratch and exchange buffers are reused by the next line

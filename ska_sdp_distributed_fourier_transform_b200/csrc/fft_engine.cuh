@@ -40,6 +40,30 @@ namespace swiftly {
 // two thread groups of one CTA, so that one group moves data through shared memory (LSU
 // bound) exactly while the other one runs its butterflies (FP64 bound).  acquire() must be
 // at least as strong as the barrier itself (everybody of the transform has arrived).
+// A storer functor is called as st(k, value).  It may instead take st(k, value, it, r) -- the
+// butterfly (it) and output (r) numbers of the last pass, compile-time constants after
+// unrolling, with k = j0 + it * T + r * NS -- which lets it derive per-output factors (e.g. the
+// twiddles of a split transform's combine step) by recurrence instead of loading each one.
+template <class St>
+SW_HD void call_store(St& st, int k, cplx v, int it, int r) {
+    if constexpr (std::is_invocable_v<St&, int, cplx, int, int>)
+        st(k, v, it, r);
+    else
+        st(k, v);
+}
+
+// geometry of the LAST pass of the N-point plan: radix, sub-transform size, butterflies per thread
+template <int N>
+struct LastPass {
+    static constexpr int passes_radix16 = (N >= 65536) ? 4 : (N >= 4096) ? 3 : (N >= 256) ? 2 : 1;
+    static constexpr int pow16 = passes_radix16 == 4 ? 65536 : passes_radix16 == 3 ? 4096
+                                 : passes_radix16 == 2 ? 256 : 16;
+    // N = 16^a * R with R in {1 (then the last pass is radix 16), 2, 4, 8}
+    static constexpr int R = (N == pow16) ? 16 : N / pow16;
+    static constexpr int NS = N / R;
+    static constexpr int ITERS = 16 / R;
+};
+
 template <class S, class = void>
 struct HasPhaseHooks : std::false_type {};
 template <class S>
@@ -288,7 +312,7 @@ SW_HD void stockham_tail(int lt, double* sm, const cplx* tw, cplx* v, St& st, Sy
             const int j = lt + it * T;
             const int base = (j / NS) * (NS * R) + (j & (NS - 1));
 #pragma unroll
-            for (int r = 0; r < R; ++r) st(base + r * NS, v[it * R + r]);
+            for (int r = 0; r < R; ++r) call_store(st, base + r * NS, v[it * R + r], it, r);
         }
     } else {
         // everybody has read the imaginary parts before the buffer is rewritten (with hooks
@@ -343,7 +367,7 @@ SW_HD void stockham_tail_cx(int lt, cplx* sm, const cplx* tw, cplx* v, St& st, S
             const int j = lt + it * T;
             const int base = (j / NS) * (NS * R) + (j & (NS - 1));
 #pragma unroll
-            for (int r = 0; r < R; ++r) st(base + r * NS, v[it * R + r]);
+            for (int r = 0; r < R; ++r) call_store(st, base + r * NS, v[it * R + r], it, r);
         }
     } else {
         if constexpr (!HOOKS) sync();
@@ -371,7 +395,7 @@ SW_HD void line_fft(int lt, double* sm, const cplx* tw, Ld& ld, St& st, Sync& sy
     Radix<R, DIR>::run(v);
     if constexpr (R == N) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) st(lt * R + r, v[r]);  // N == 16: lt == 0
+        for (int r = 0; r < R; ++r) call_store(st, lt * R + r, v[r], 0, r);  // N == 16: lt == 0
     } else {
         stockham_tail<N, R, R, DIR>(lt, sm, tw, v, st, sync);
     }

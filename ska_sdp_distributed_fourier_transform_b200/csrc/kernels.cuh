@@ -47,6 +47,10 @@ struct PrepareFacetOp {
     // optional input row map (fused extract_from_facet along the OTHER axis,
     // api_helper.py:200-210): input line = (rm_base + ((line - rm_s_m) mod rm_m)) mod rm_mod
     int rm_m, rm_s_m, rm_base, rm_mod;
+    // optional per-LINE weights applied to the output (the Fb window of the OTHER axis folded
+    // into this pass: the fused forward path keeps its prepared facets pre-windowed so that the
+    // next kernel, K2, does not have to fetch a window value per sample)
+    const double* lw;
     SW_HD cplx load(int64_t line, int q) const {
         int k = wrap_add(q, shift_in, n);
         if (k >= fs) return mk(0.0, 0.0);
@@ -56,7 +60,8 @@ struct PrepareFacetOp {
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         int pc = wrap_add(p, n / 2, n);
-        st_stream(g.out + line * g.out_ls + (int64_t)pc * g.out_es, cscale(v, scale));
+        const double f = lw ? scale * ldg_d(lw + line) : scale;
+        st_stream(g.out + line * g.out_ls + (int64_t)pc * g.out_es, cscale(v, f));
     }
     SW_HD void prefetch(int64_t line, int q) const {
         int k = wrap_add(q, shift_in, n);
@@ -105,6 +110,7 @@ struct PrepareFacetPassBOp {
     Lines g;  // g.in: scratch T; g.out: prepared facet (n rows, row stride out_es)
     int n, n1, n2, ncols;
     double scale;
+    const double* lw;  // optional per-column weights (see PrepareFacetOp::lw)
     SW_HD cplx load(int64_t line, int q) const {
         const int k1 = (int)(line / ncols);
         const int c = (int)(line - (int64_t)k1 * ncols);
@@ -114,7 +120,8 @@ struct PrepareFacetPassBOp {
         const int k1 = (int)(line / ncols);
         const int c = (int)(line - (int64_t)k1 * ncols);
         int pc = wrap_add(k1 + n1 * k2, n / 2, n);
-        st_stream(g.out + (int64_t)pc * g.out_es + c, cscale(v, scale));
+        const double f = lw ? scale * ldg_d(lw + c) : scale;
+        st_stream(g.out + (int64_t)pc * g.out_es + c, cscale(v, f));
     }
 };
 
@@ -132,7 +139,7 @@ struct ColumnFacet {
 struct ExtractColumnsOp {
     Lines g;           // only n_lines (= n_facets * lines_per) is used
     ColumnFacet fac[SW_MAX_COLUMN_FACETS];
-    const double* fb;  // full Fb table
+    const double* fb;  // full Fb table, or null: the rows are already Fb weighted
     int n;             // yN
     int lines_per;     // m
     double scale;      // 1 / yN
@@ -144,7 +151,8 @@ struct ExtractColumnsOp {
         int k = wrap_add(q, F.shift_in, n);
         if (k >= F.fs) return mk(0.0, 0.0);
         int64_t row = wrap_add(rm_base, wrap_sub(l, rm_s_m, lines_per), n);
-        return cscale(ld_stream(F.in + row * F.in_ls + k), ldg_d(fb + F.fb_off + k));
+        cplx x = ld_stream(F.in + row * F.in_ls + k);
+        return fb ? cscale(x, ldg_d(fb + F.fb_off + k)) : x;
     }
     SW_HD void store(int64_t line, int p, cplx v) const {
         const int f = (int)(line / lines_per);

@@ -1,22 +1,30 @@
-// SwiFTly B200 -- ping-pong variant of the fused subgrid axis kernel.
+// SwiFTly B200 -- two-group variant of the fused subgrid axis kernel.
 //
 // Same mathematics and the same parameters as SubgridAxisKernel (kernels.cuh): for every
 // output line the m-point transforms of the sources are overlap-added (Fn weighted) into an
 // xM accumulator in shared memory, the xM-point inverse transform runs from there and the
 // wanted xA samples are stored (api_helper.py:73-112, core.py:224-325).
 //
-// What is different is how an SM is kept busy.  A line alternates between shared-memory
-// exchange phases (LSU bound) and butterfly phases (FP64 bound).  With independent CTAs
-// the two co-resident lines of an SM fall into lockstep -- both exchange, then both compute
-// -- and each pipe idles while the other one works (round 1: LSU 60 % + FP64 39 % of the
-// time).  Here ONE CTA holds two thread groups, each with its own line, its own accumulator
-// and exchange buffers, and the groups pass an "LSU token" through a pair of named barriers
-// (bar.sync / bar.arrive): a group runs an exchange phase only while it holds the token and
-// hands it over when the phase ends, so the groups are forced into anti-phase -- group 0
-// moves data while group 1 multiplies, and vice versa.
+// ONE persistent CTA per SM holds two thread groups, each with its own line, accumulator and
+// exchange buffers (209 KiB of shared memory at m = 1024, xM = 4096).  What the layout buys:
+//   * finished lines leave through the TMA engine: they are staged in the group's (idle) work
+//     area and scattered by bulk tensor stores with ANY output strides -- transposed strips
+//     for the axis-0 kernel, the owner's receive buffer on a peer GPU -- at no LSU cost;
+//   * the next windows are pulled into L2 by bulk prefetches (one instruction per window);
+//   * the xM-point transform exchanges COMPLEX samples (one trip per pass, two barriers)
+//     through the accumulator's own storage: the accumulator is dead once the first pass has
+//     loaded it;
+//   * per-group output pointers / tensor maps (groups in different buffers).
 //
-// The xM-point transform exchanges COMPLEX samples (one trip per pass, two barriers) through
-// the accumulator's own storage: the accumulator is dead once the first pass has loaded it.
+// TOKENS (kept as a measured experiment, off by default): a line alternates between
+// shared-memory exchange phases (LSU bound) and butterfly phases (FP64 bound); with the token
+// the groups are forced into anti-phase through a pair of named barriers (bar.sync /
+// bar.arrive), one exchanging while the other multiplies.  Measured on B200 (cfg4, 8 facet
+// rows): 0.650 ms with tokens against 0.575 ms without.  tools/pipe_lab.cu shows why: a single
+// 256-thread group reaches neither pipe's peak alone (exchange 1040 cycles per pass alone, 813
+// per line when two groups exchange together; butterflies 1280 alone, 910 shared) -- the phases
+// are latency bound at two warps per scheduler, so serialising them loses more than the
+// overlap gains.
 #pragma once
 
 #include "kernels.cuh"
@@ -66,8 +74,13 @@ struct SubgridAxisKernelPP {
     int tma_box;                                       // samples per bulk tensor store
     int tma_slot_line, tma_slot_elem, tma_slot_group;  // coordinate slots (1..3)
     int tma_per_group;                 // one tensor map per group (groups in different buffers)
+    int pf_mode;                       // L2 prefetch: 0 bulk at the first exchange (default),
+                                       // 1 none, 2 per-thread prefetch at the start of the round
     cplx* out_g[SW_MAX_GROUPS];        // optional per-group output base (null: out + g * out_gs)
-    TensorMap4 out_map[SW_MAX_GROUPS];  // [0] covers all groups unless tma_per_group
+    // tensor maps travel as a separate __grid_constant__ kernel parameter (ctx.tmaps)
+    struct Maps {
+        TensorMap4 out_map[SW_MAX_GROUPS];  // [0] covers all groups unless tma_per_group
+    };
 
     // barrier ids: 0 = whole CTA, 1 + g = group g, 3 + g * CONC + c = transform c of group g,
     // 11 + g = token of group g
@@ -75,11 +88,35 @@ struct SubgridAxisKernelPP {
     struct GroupSync {
         const Ctx& ctx;
         int bar_id, bar_count;  // barrier of the threads that share the exchange buffer
-        int grp;
+        int grp, t;
+        // set at the start of a line whose predecessor left through the TMA engine: the first
+        // exchange of the line is the first use of the work area (= the staging buffer), so
+        // only THERE -- after the line's global loads and first butterflies -- thread 0 makes
+        // sure the bulk stores have read it, and the barrier is widened to the whole group
+        bool tma_pending;
+        // L2 prefetch of the transform's NEXT window, issued at the first exchange of the round
+        // and not together with the round's own loads: both at once would just double the burst
+        // every SM sends to DRAM at the same moment (measured: the load phase took 4.7-5.5 k
+        // cycles, the time 2 x 64 KiB need at an SM's fair share of the HBM bandwidth)
+        const void* pf_ptr[2];
+        uint32_t pf_bytes[2];
         SW_HD void operator()() const { ctx.group_sync(bar_id, bar_count); }
-        // start of an exchange phase: wait for the token (the other group's release); the
-        // wait is also a barrier over the whole group
-        SW_HD void acquire() const {
+        // start of an exchange phase: with TOKENS wait for the token (the other group's
+        // release); either way a barrier over (at least) the transform's threads
+        SW_HD void acquire() {
+            if (pf_bytes[0]) {
+                ctx.bulk_prefetch_l2(pf_ptr[0], pf_bytes[0]);
+                if (pf_bytes[1]) ctx.bulk_prefetch_l2(pf_ptr[1], pf_bytes[1]);
+                pf_bytes[0] = pf_bytes[1] = 0;
+            }
+            if (tma_pending) {
+                tma_pending = false;
+                if (t == 0) ctx.bulk_wait_read();
+                if (!TOKENS) {
+                    ctx.group_sync(1 + grp, T_X);
+                    return;
+                }
+            }
             if (TOKENS)
                 ctx.group_sync(11 + grp, THREADS);
             else
@@ -98,9 +135,9 @@ struct SubgridAxisKernelPP {
         double* work = (double*)((cplx*)ctx.smem + (size_t)GROUPS * ACCS) + (size_t)grp * WORK;
         const int c = t / T_M;
         const int lt = t % T_M;
-        GroupSync<Ctx> gsync{ctx, 1 + grp, T_X, grp};
+        GroupSync<Ctx> gsync{ctx, 1 + grp, T_X, grp, t, false, {nullptr, nullptr}, {0, 0}};
         GroupSync<Ctx> msync{ctx, SUB_BARRIERS ? 3 + grp * CONC + c : 1 + grp,
-                             SUB_BARRIERS ? T_M : T_X, grp};
+                             SUB_BARRIERS ? T_M : T_X, grp, t, false, {nullptr, nullptr}, {0, 0}};
         // group 1 hands the token to group 0 to start with
         if (TOKENS && grp == 1) ctx.group_arrive(11, THREADS);
         const int64_t pairs = (n_lines + GROUPS - 1) / GROUPS;  // line pairs per source group
@@ -109,11 +146,9 @@ struct SubgridAxisKernelPP {
             const int sgrp = (int)(gl / pairs);
             const int64_t line = (gl - (int64_t)sgrp * pairs) * GROUPS + grp;
             const bool line_ok = line < n_lines;
-            if (tma_out) {
-                // the previous line's bulk stores must have read the staging (= work) buffer
-                if (t == 0) ctx.bulk_wait_read();
-                gsync();
-            }
+            // the previous line's bulk stores must have read the staging (= work) buffer before
+            // the first exchange of this line writes it (see GroupSync::acquire)
+            msync.tma_pending = tma_out != 0;
             if (!first_round_tiles) {
                 for (int i = t; i < XM; i += T_X) acc[i] = mk(0.0, 0.0);
                 gsync();
@@ -150,10 +185,10 @@ struct SubgridAxisKernelPP {
                 };
                 // L2 prefetch of what this transform loads next -- the next round of this line, or
                 // the first round of the group's next line: ONE bulk prefetch per window
-                // (cp.async.bulk.prefetch.L2, issued by the transform's first thread; the window
-                // is M contiguous samples, in two pieces when it wraps), no per-thread
-                // prefetch instructions and no LSU wavefronts
-                if (lt == 0) {
+                // (cp.async.bulk.prefetch.L2; the window is M contiguous samples, in two pieces
+                // when it wraps), prepared here by the transform's first thread and issued at
+                // the round's first exchange (GroupSync::acquire)
+                if (pf_mode == 2 || (pf_mode == 0 && lt == 0)) {
                     int pslot0 = slot0 + CONC, psgrp = sgrp;
                     int64_t pline = line;
                     if (pslot0 >= n_slots) {
@@ -169,9 +204,19 @@ struct SubgridAxisKernelPP {
                             const cplx* pb = ps.base + pline * ps.ls;
                             const int first = ps.wbase;  // samples [first, first + M) mod wmod
                             const int n1 = first + M <= ps.wmod ? M : ps.wmod - first;
-                            ctx.bulk_prefetch_l2(pb + first, (uint32_t)n1 * (uint32_t)sizeof(cplx));
-                            if (n1 < M)
-                                ctx.bulk_prefetch_l2(pb, (uint32_t)(M - n1) * (uint32_t)sizeof(cplx));
+                            if (pf_mode == 2) {
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) {
+                                    int tc = wrap_add(lt + r * T_M, M / 2, M);
+                                    int idx = wrap_add(ps.wbase, wrap_sub(tc, ps.s_m, M), ps.wmod);
+                                    prefetch_l2(pb + idx);
+                                }
+                            } else {
+                            msync.pf_ptr[0] = pb + first;
+                            msync.pf_bytes[0] = (uint32_t)n1 * (uint32_t)sizeof(cplx);
+                            msync.pf_ptr[1] = pb;
+                            msync.pf_bytes[1] = (uint32_t)(M - n1) * (uint32_t)sizeof(cplx);
+                            }
                         }
                     }
                 }
@@ -210,7 +255,7 @@ struct SubgridAxisKernelPP {
                 int c[4] = {0, 0, 0, 0};
                 c[tma_slot_line] = (int)line;
                 c[tma_slot_group] = tma_per_group ? 0 : sgrp;
-                const TensorMap4* map = &out_map[tma_per_group ? sgrp : 0];
+                const TensorMap4* map = &((const Maps*)ctx.tmaps)->out_map[tma_per_group ? sgrp : 0];
                 for (int r0 = 0; r0 < sz; r0 += tma_box) {
                     c[tma_slot_elem] = r0;
                     ctx.tensor_store(map, (const cplx*)work + r0, c[1], c[2], c[3]);

@@ -186,7 +186,7 @@ class SwiftlyForwardSharded:
             for i, facet in zip(self.local_idx, uploads):
                 cfg = self.facet_configs[i]
                 self.BF_Fs[i] = self.core.prepare_facet(
-                    facet, cfg.off0, axis=0, out=self._bf_f_buffers.get(i))
+                    facet, cfg.off0, axis=0, out=self._bf_f_buffers.get(i), window_lines=True)
                 self.launches += 1
                 del facet
             self._local_facets = {}
@@ -201,7 +201,8 @@ class SwiftlyForwardSharded:
             outs = self.core.extract_columns(
                 [self.BF_Fs[i] for i in self.local_idx], off0,
                 [self.facet_configs[i].off1 for i in self.local_idx],
-                outs=None if reuse is None else [reuse[i] for i in self.local_idx])
+                outs=None if reuse is None else [reuse[i] for i in self.local_idx],
+                prewindowed=True)
             cached = dict(zip(self.local_idx, outs))
             self.launches += 1
             self.lru.set(off0, cached)

@@ -78,6 +78,7 @@ struct EmuBlock;
 struct HostCtx {
     int tid, bid, nblocks;
     char* smem;
+    const void* tmaps;
     EmuBlock* blk;
     inline void sync() const;
     // named barriers with the hardware's counting semantics (bar.sync / bar.arrive a, b):
@@ -175,7 +176,21 @@ static void emu_entry(void* body, HostCtx& ctx) {
 }
 
 template <class Body>
+inline cudaError_t launch_body_impl(const Body& body, const void* tmaps, int grid, size_t smem_bytes);
+
+template <class Body>
 inline cudaError_t launch_body(const Body& body, int grid, size_t smem_bytes, cudaStream_t) {
+    return launch_body_impl(body, nullptr, grid, smem_bytes);
+}
+
+template <class Body>
+inline cudaError_t launch_body_maps(const Body& body, const typename Body::Maps& maps, int grid,
+                                    size_t smem_bytes, cudaStream_t) {
+    return launch_body_impl(body, &maps, grid, smem_bytes);
+}
+
+template <class Body>
+inline cudaError_t launch_body_impl(const Body& body, const void* tmaps, int grid, size_t smem_bytes) {
     const int T = Body::THREADS;
     const size_t STACK = 256 * 1024;
     EmuBlock blk;
@@ -200,6 +215,7 @@ inline cudaError_t launch_body(const Body& body, int grid, size_t smem_bytes, cu
             blk.hctx[t].bid = bid;
             blk.hctx[t].nblocks = grid;
             blk.hctx[t].smem = smem;
+            blk.hctx[t].tmaps = tmaps;
             blk.hctx[t].blk = &blk;
         }
         g_emu_block = &blk;

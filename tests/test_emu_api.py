@@ -48,8 +48,8 @@ def test_emu_many_sources():
 
 @pytest.mark.parametrize("sg_variant", [0, 1, 2, 5])
 def test_emu_forward_backward_vs_oracle_kernel_variants(sg_variant):
-    """Every variant of the fused subgrid kernel (0: ping-pong + tokens + TMA tensor stores,
-    1: round-1 kernel, 2: ping-pong without tokens, 5: ping-pong with direct stores)."""
+    """Every variant of the fused subgrid kernel (0: two thread groups + TMA tensor stores,
+    1: round-1 kernel, 2: two groups with the LSU token, 5: two groups, direct stores)."""
     api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)
 
 

@@ -122,3 +122,17 @@ def test_emu_non_power_of_two_lengths(emu_core_cls, p):
     pc.check_1d_chain(core, oracle, yB - 1, xA - 1, -2 * Ny, 4 * Nx, rng)
     pc.check_2d_axis(core, oracle, yB, 0, 5, Ny, -Nx, rng)
     pc.check_2d_axis(core, oracle, yB, 1, 5, Ny, -Nx, rng)
+
+
+def test_emu_prepare_facet_column_tiles(emu_core_cls):
+    """Two-pass prepare_facet along the strided axis in several column tiles (the debug hook
+    shrinks the tile to 32 columns: 3 full tiles and a ragged one for 110 columns)."""
+    import ctypes
+
+    core, oracle = pc.make_pair(emu_core_cls, W=13.5625, N=1024, xM=256, yN=512)
+    core._lib.swiftly_b200_debug_sg_variant.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    core._lib.swiftly_b200_debug_sg_variant(core._plan, 10)
+    rng = numpy.random.default_rng(10)
+    facet = pc.rand_c(rng, 256, 110)
+    got = core.prepare_facet(facet, 3 * core.facet_off_step, axis=0)
+    pc.close(got, oracle.prepare_facet(facet, 3 * core.facet_off_step, axis=0), what="tiled")

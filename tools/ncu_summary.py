@@ -31,12 +31,14 @@ STALL = 'smsp__average_warp'
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[0]
+units = dict(zip(hdr, rows[1]))  # ncu's unit row (ns / us, byte / Mbyte / Gbyte, %, ...)
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     print(d.get('Kernel Name', '')[:150])
     for k in KEYS:
         if k in d:
-            print(f"   {k} = {d[k]}")
+            u = units.get(k, '')
+            print(f"   {k} = {d[k]}" + (f" [{u}]" if u else ''))
     st = sorted(((float(v.replace(',', '')), k) for k, v in d.items()
                  if k.startswith('smsp__average_warps_issue_stalled') and v not in ('', 'n/a')), reverse=True)
     for v, k in st[:7]:

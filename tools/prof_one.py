@@ -28,7 +28,8 @@ elif which == "f2":
         core.extract_columns(bfs, 4096, [yB * i for i in range(nf)], outs=outs)
 elif which in ("f3", "f4"):
     nmbf = [torch.randn(m, yN, dtype=torch.complex128, device=dev) for _ in range(nf)]
-    strips = torch.randn(nf, m, xA, dtype=torch.complex128, device=dev)
+    # strips transposed (contribution index contiguous), as the product stores them
+    strips = torch.randn(nf, xA, m, dtype=torch.complex128, device=dev).transpose(1, 2)
     out = torch.empty(xA, xA, dtype=torch.complex128, device=dev)
     for _ in range(reps):
         if which == "f3":

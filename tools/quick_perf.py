@@ -33,11 +33,16 @@ def timeit(fn, reps=5):
     return min(ts), sum(ts) / len(ts)
 
 
+import ctypes  # noqa: E402
+
+core._lib.swiftly_b200_debug_sg_variant.argtypes = [ctypes.c_void_p, ctypes.c_int]
 facet = torch.randn(yB, yB, dtype=torch.complex128, device=dev)
 bf = torch.empty(yN, yB, dtype=torch.complex128, device=dev)
-t, ta = timeit(lambda: core.prepare_facet(facet, 0, axis=0, out=bf), 3)
 by = 16 * (yB * yB + yN * yB)
-print(f"F1 prepare_facet ax0: {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
+for variant, name in ((8, "one tile (round 1)"), (9, "128 MiB column tiles"), (0, "64 MiB column tiles")):
+    core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
+    t, ta = timeit(lambda: core.prepare_facet(facet, 0, axis=0, out=bf), 3)
+    print(f"F1 prepare_facet ax0 [{name}]: {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
 del facet
 nmbf = [torch.empty(m, yN, dtype=torch.complex128, device=dev) for _ in range(nf)]
 t, ta = timeit(lambda: core.extract_column(bf, 4096, 8192, out=nmbf[0]))
@@ -45,9 +50,6 @@ by = 16 * (m * yB + m * yN)
 print(f"F2 extract_column:   {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
 for i in range(1, nf):
     core.extract_column(bf, 4096, 8192 * i, out=nmbf[i])
-import ctypes  # noqa: E402
-
-core._lib.swiftly_b200_debug_sg_variant.argtypes = [ctypes.c_void_p, ctypes.c_int]
 bfs = [bf] * nf
 offs = [yB * i for i in range(nf)]
 by = 16 * (m * yB + m * yN) * nf
@@ -62,10 +64,13 @@ for variant, name in ((4, "round-1 kernel"), (7, "TMA rows, 2 x (yN/2), swizzled
     else:
         print(f"   max |diff|: {(nmbf[3] - keep).abs().max().item():.3e} (max |ref| {keep.abs().max().item():.3e})")
 core._lib.swiftly_b200_debug_sg_variant(core._plan, 0)
+t, ta = timeit(lambda: core.extract_columns(bfs, 4096, offs, outs=nmbf, prewindowed=True))
+print(f"F2 extract_columns x{nf} [default kernel, PRE-WINDOWED rows (no Fb fetch)]: {t:.3f} ms (avg {ta:.3f})  frac {by/t*1e3/HBM:.3f}")
+core.extract_columns(bfs, 4096, offs, outs=nmbf)
 strips = torch.empty(nf, m, xA, dtype=torch.complex128, device=dev)
 srcs = [(nmbf[i], i * yB) for i in range(nf)]
 ref = None
-for variant, name in ((1, "round-1 kernel"), (2, "ping-pong layout, no tokens"), (0, "ping-pong + tokens")):
+for variant, name in ((1, "round-1 kernel"), (2, "two groups + LSU token"), (0, "two groups (default)")):
     core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
     t, ta = timeit(lambda: core.sum_finish_axis(srcs, strips[0], axis=1, subgrid_off=2048))
     by = 16 * (nf * m * m + m * xA)
@@ -85,16 +90,23 @@ srcs0 = [(strips[i], i * yB) for i in range(nf)]
 t, ta = timeit(lambda: core.sum_finish_axis(srcs0, out, axis=0, subgrid_off=4096))
 by = 16 * (nf * m * xA + xA * xA)
 print(f"F4 sum_finish ax0 ({nf} src): {t:.3f} ms (avg {ta:.3f})  {by/t*1e3/1e9:.0f} GB/s  frac {by/t*1e3/HBM:.3f}")
-# transposed strips (what the product uses): finished lines leave through the TMA engine
+# transposed strips (what the product uses): finished lines leave through the TMA engine.
+# Distinct prepared facets per group as in a real step (64 x 256 MiB: no L2 reuse across groups).
 ref0 = out.clone()
 strips_t = torch.empty(nf, xA, m, dtype=torch.complex128, device=dev).transpose(1, 2)
-for variant, name in ((5, "ping-pong + tokens, direct 16-byte stores"), (2, "ping-pong, no tokens, TMA tensor stores"),
-                      (0, "ping-pong + tokens, TMA tensor stores")):
+big = [[torch.randn(m, yN, dtype=torch.complex128, device=dev) for _ in range(nf)] for _ in range(nf)]
+groups = [[(big[g][i], i * yB) for i in range(nf)] for g in range(nf)]
+for variant, name in ((1, "round-1 kernel"), (11, "two groups, no L2 prefetch"),
+                      (12, "two groups, per-thread prefetch"), (0, "two groups, bulk prefetch (default)")):
     core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
-    t, ta = timeit(lambda: core.sum_finish_axis_grouped([srcs] * nf, strips_t, axis=1, subgrid_off=2048))
+    t, ta = timeit(lambda: core.sum_finish_axis_grouped(groups, strips_t, axis=1, subgrid_off=2048))
     by = 16 * nf * (nf * m * m + m * xA)
-    print(f"F3 grouped x{nf} -> TRANSPOSED strips [{name}]: {t:.3f} ms (avg {ta:.3f})  frac {by/t*1e3/HBM:.3f}")
-    print(f"   max |diff| vs row-major strips: {(strips_t - ref).abs().max().item():.3e}")
+    print(f"F3 grouped x{nf}, distinct facets -> TRANSPOSED strips [{name}]: {t:.3f} ms (avg {ta:.3f})  frac {by/t*1e3/HBM:.3f}")
+del big, groups
+for i in range(nf):
+    core.sum_finish_axis(srcs, strips_t[i], axis=1, subgrid_off=2048)
+for variant, name in ((5, "two groups, direct 16-byte stores"), (0, "two groups, TMA tensor stores (default)")):
+    core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
     srcs0t = [(strips_t[i], i * yB) for i in range(nf)]
     t, ta = timeit(lambda: core.sum_finish_axis(srcs0t, out, axis=0, subgrid_off=4096))
     by = 16 * (nf * m * xA + xA * xA)
