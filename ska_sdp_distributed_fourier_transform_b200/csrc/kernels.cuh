@@ -93,17 +93,36 @@ struct PrepareFacetPassAOp {
         if (k >= fs) return mk(0.0, 0.0);
         return cscale(ld_stream(g.in + (int64_t)k * g.in_es + c), ldg_d(fb + k));
     }
-    SW_HD void store(int64_t line, int k1, cplx v) const {
+    // The inter-pass twiddles w^(j2 k1) of a thread's outputs k1 = j0 + it * T + r * NS follow
+    // by recurrence from three table values that depend on (j2, thread) only: prep() loads them
+    // BEFORE the transform, together with the data, instead of one dependent table load per
+    // output after it (round 1: a second exposed L2 round trip per line, long-scoreboard 6.4
+    // warps per issue at 31 % of the DRAM bandwidth).
+    struct Tw {
+        cplx base, step_it, step_r;
+    };
+    SW_HD cplx root(int t) const {  // exp(+2 pi i t / n), 0 <= t < n  (inverse direction)
+        const bool neg = t >= n / 2;
+        cplx w = ldg_c(twf + (neg ? t - n / 2 : t));
+        w.y = -w.y;
+        return neg ? mk(-w.x, -w.y) : w;
+    }
+    SW_HD Tw prep(int64_t line, int j0, int T, int NS) const {
+        const int j2 = (int)(line / ncols);
+        Tw t;
+        t.base = root(j2 * j0);        // all exponents < n1 * n2 = n
+        t.step_it = root(j2 * T);
+        t.step_r = root((j2 * NS) % n);
+        return t;
+    }
+    SW_HD void store_w(int64_t line, int k1, cplx v, cplx w) const {
         const int j2 = (int)(line / ncols);
         const int c = (int)(line - (int64_t)j2 * ncols);
-        int t = j2 * k1;  // < n
-        const bool neg = t >= n / 2;
-        if (neg) t -= n / 2;
-        cplx w = ldg_c(twf + t);
-        w.y = -w.y;  // inverse direction
-        cplx r = cmul(v, w);
-        if (neg) r = mk(-r.x, -r.y);
-        g.out[((int64_t)k1 * n2 + j2) * ncols + c] = r;
+        g.out[((int64_t)k1 * n2 + j2) * ncols + c] = cmul(v, w);
+    }
+    SW_HD void store(int64_t line, int k1, cplx v) const {
+        const int j2 = (int)(line / ncols);
+        store_w(line, k1, v, root(j2 * k1));
     }
 };
 struct PrepareFacetPassBOp {
@@ -362,6 +381,12 @@ struct PrepareSubgridOp {
     }
 };
 
+// ops that derive per-output factors by recurrence (prep / store_w, see PrepareFacetPassAOp)
+template <class Op, class = void>
+struct HasTwiddlePrep : std::false_type {};
+template <class Op>
+struct HasTwiddlePrep<Op, std::void_t<typename Op::Tw>> : std::true_type {};
+
 // ------------------------------------------------------------------ line kernels
 // NFFT-point transform of a batch of lines; LPC lines per CTA, T = NFFT/16
 // threads per line.  LINE_FASTEST selects which of (line, thread-in-line) varies
@@ -390,10 +415,26 @@ struct LineKernel {
             const int64_t line = line0 + l;
             const bool active = line < op.g.n_lines;
             auto ld = [&](int q) { return active ? op.load(line, q) : mk(0.0, 0.0); };
-            auto st = [&](int p, cplx v) {
-                if (active) op.store(line, p, v);
-            };
-            line_fft<NFFT, DIR>(lt, sm, tw, ld, st, sync);
+            if constexpr (HasTwiddlePrep<Op>::value) {
+                typedef LastPass<NFFT> LP;
+                typename Op::Tw tws = op.prep(active ? line : 0, lt, T, LP::NS);
+                cplx w_it = tws.base, w = tws.base;
+                auto st = [&](int p, cplx v, int it, int r) {
+                    if (r == 0) {
+                        if (it > 0) w_it = cmul(w_it, tws.step_it);
+                        w = w_it;
+                    } else {
+                        w = cmul(w, tws.step_r);
+                    }
+                    if (active) op.store_w(line, p, v, w);
+                };
+                line_fft<NFFT, DIR>(lt, sm, tw, ld, st, sync);
+            } else {
+                auto st = [&](int p, cplx v) {
+                    if (active) op.store(line, p, v);
+                };
+                line_fft<NFFT, DIR>(lt, sm, tw, ld, st, sync);
+            }
             ctx.sync();  // smem is reused by the next line
         }
     }
