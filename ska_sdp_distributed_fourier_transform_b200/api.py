@@ -381,6 +381,9 @@ class SwiftlyForward:
             rows.setdefault(cfg.off0, []).append(idx)
         self._rows = list(rows.items())
         self._strips = None
+        self._prep0 = None
+        self._prep1 = None
+        self._masks = {}
         self._fused = bool(getattr(self.core, "fused_forward_supported", lambda: False)())
 
     # -- stage 1: prepare every facet along axis 0 (once) --------------------------------
@@ -438,19 +441,36 @@ class SwiftlyForward:
             # scattered into this layout by the TMA engine (bulk tensor stores)
             self._strips = torch.empty((shape[0], shape[2], shape[1]), dtype=torch.complex128,
                                        device=self.device).transpose(1, 2)
-        mask0 = _device_mask(sg.mask0, self.device)
-        mask1 = _device_mask(sg.mask1, self.device)
-        core.sum_finish_axis_grouped(
-            [[(NMBF_BFs[j], self.facet_tasks[j][0].off1) for j in members]
-             for _, members in self._rows],
-            self._strips, axis=1, subgrid_off=sg.off1, mask=mask1,
-        )
+            self._prep0 = None
+        mask0 = self._mask(sg, 0)
+        mask1 = self._mask(sg, 1)
+        # the argument blocks are built once per subgrid column (axis 1) / once per transform
+        # (axis 0) and reused: per subgrid only offsets, masks and the output pointer change
+        key = id(NMBF_BFs)
+        if self._prep1 is None or self._prep1[0] != key or self._prep1[1] != sg.size:
+            groups = [[(NMBF_BFs[j], self.facet_tasks[j][0].off1) for j in members]
+                      for _, members in self._rows]
+            self._prep1 = (key, sg.size, core.prepare_sum_finish(
+                groups, 1, m, sg.size, (self._strips.stride(1), self._strips.stride(2))), NMBF_BFs)
+        nrows = len(self._rows)
+        self._prep1[2].launch([sg.off1] * nrows, [mask1] * nrows, out=self._strips,
+                              out_group_stride=self._strips.stride(0))
         out = torch.empty((sg.size, sg.size), dtype=torch.complex128, device=self.device)
-        core.sum_finish_axis(
-            [(self._strips[r], off0) for r, (off0, _) in enumerate(self._rows)],
-            out, axis=0, subgrid_off=sg.off0, mask=mask0,
-        )
+        if self._prep0 is None or self._prep0[0] != sg.size:
+            sources = [[(self._strips[r], off0) for r, (off0, _) in enumerate(self._rows)]]
+            self._prep0 = (sg.size, core.prepare_sum_finish(
+                sources, 0, sg.size, sg.size, (out.stride(1), out.stride(0))))
+        self._prep0[1].launch([sg.off0], [mask0], out=out)
         return out
+
+    def _mask(self, sg, axis):
+        """Device mask of a subgrid along ``axis`` (None when absent or all ones), cached by
+        (axis, offset, size): a cover has only a few distinct masks per axis."""
+        off = sg.off0 if axis == 0 else sg.off1
+        key = (axis, off, sg.size)
+        if key not in self._masks:
+            self._masks[key] = _device_mask(sg.mask0 if axis == 0 else sg.mask1, self.device)
+        return self._masks[key]
 
     def get_subgrid_task(self, subgrid_config):
         """Enqueue the computation of one subgrid and return its handle."""

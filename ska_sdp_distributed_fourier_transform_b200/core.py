@@ -34,6 +34,73 @@ def _is_tensor(a):
     return torch is not None and isinstance(a, torch.Tensor)
 
 
+class PreparedSumFinish:
+    """Reusable argument block of a grouped ``sum_finish_axis`` launch (see
+    :meth:`SwiftlyCoreB200.prepare_sum_finish`)."""
+
+    # pylint: disable=too-many-instance-attributes,protected-access
+    def __init__(self, core, groups, axis, n_lines, size, out_strides):
+        if axis not in (0, 1):
+            raise ValueError(f"Invalid axis {axis}")
+        self.core = core
+        self.axis = axis
+        self.n_groups = len(groups)
+        other = 1 - axis
+        flat = [s for grp in groups for s in grp]
+        self._keep = [t for t, _ in flat]  # the sources must outlive the block
+        self._arr = (_lib.Source * max(1, len(flat)))()
+        for i, (t, facet_off) in enumerate(flat):
+            core._check_tensor(t)
+            if t.dtype != torch.complex128 or t.dim() != 2:
+                raise ValueError("sources must be 2-D complex128 device tensors")
+            if t.shape[other] != n_lines:
+                raise ValueError(f"source has {t.shape[other]} lines, output {n_lines}")
+            self._arr[i] = _lib.Source(t.data_ptr(), t.stride(other), t.stride(axis),
+                                       t.shape[axis], int(facet_off))
+        self._sizes = (ctypes.c_int32 * self.n_groups)(*[len(g) for g in groups])
+        self._offs = (ctypes.c_int64 * self.n_groups)()
+        self._mptrs = (ctypes.c_void_p * self.n_groups)()
+        self._optrs = (ctypes.c_void_p * self.n_groups)()
+        self._dout = _lib.Lines(0, int(n_lines), int(size), int(out_strides[0]),
+                                int(out_strides[1]), _lib.DEVICE)
+        self._device = flat[0][0].device if flat else None
+
+    def launch(self, subgrid_offs, masks=None, out=None, out_group_stride=0, outs=None,
+               n_groups=None, out_ptrs=None, stream_of=None):
+        """Launch for the first ``n_groups`` groups (default: all).
+
+        :param subgrid_offs: one offset per group
+        :param masks: None or one float64 device tensor / None per group
+        :param out, out_group_stride: base tensor of group 0 and the stride between groups, or
+        :param outs: one output tensor per group (same shape / strides, different buffers), or
+        :param out_ptrs: their device addresses (ints) with ``stream_of`` a tensor on the device
+        """
+        n = self.n_groups if n_groups is None else int(n_groups)
+        core = self.core
+        for g in range(n):
+            self._offs[g] = int(subgrid_offs[g])
+            mk = None if masks is None else masks[g]
+            self._mptrs[g] = None if mk is None else mk.data_ptr()
+        if outs is not None or out_ptrs is not None:
+            if out_ptrs is not None:
+                for g in range(n):
+                    self._optrs[g] = out_ptrs[g]
+                stream = core._stream(stream_of)
+            else:
+                for g in range(n):
+                    self._optrs[g] = outs[g].data_ptr()
+                stream = core._stream(outs[0])
+            rc = core._lib.swiftly_b200_sum_finish_axis_scattered(
+                core._plan, self._arr, self._sizes, n, ctypes.byref(self._dout), self._optrs,
+                self._offs, self._mptrs, stream)
+        else:
+            self._dout.data = out.data_ptr()
+            rc = core._lib.swiftly_b200_sum_finish_axis_batched(
+                core._plan, self._arr, self._sizes, n, ctypes.byref(self._dout),
+                int(out_group_stride), self._offs, self._mptrs, core._stream(out))
+        _lib.check(core._lib, rc)
+
+
 class SwiftlyCoreB200:
     """Streaming distributed Fourier transform primitives, CUDA (sm_100a) backend.
 
@@ -516,6 +583,20 @@ class SwiftlyCoreB200:
             offs, mptrs, self._stream(out))
         _lib.check(self._lib, rc)
         return out
+
+    def prepare_sum_finish(self, groups, axis, n_lines, size, out_strides):
+        """Build the argument block of a grouped ``sum_finish_axis`` launch ONCE.
+
+        The streaming drivers launch the same source groups for every subgrid of a subgrid
+        column (only the subgrid offsets, masks and output buffers change); building the
+        ctypes descriptors of 64 sources costs more host time than the kernel takes on several
+        GPUs.  Returns a :class:`PreparedSumFinish`; ``launch(...)`` fills in the per-call values.
+
+        :param groups: list of source lists ``[(tensor, facet_off), ...]``
+        :param n_lines, size: lines and samples per line of ONE group's output
+        :param out_strides: ``(line_stride, elem_stride)`` of a group's output (samples)
+        """
+        return PreparedSumFinish(self, groups, axis, n_lines, size, out_strides)
 
     def sum_finish_axis(self, sources, out, axis, subgrid_off, mask=None):
         """One axis of ``sum_and_finish_subgrid`` (api_helper.py:73-112) as ONE kernel.

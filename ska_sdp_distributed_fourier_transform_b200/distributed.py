@@ -101,6 +101,10 @@ class SwiftlyForwardSharded:
         self.rows_max = max(1, max(len(r) for r in self.rank_rows))
         self.my_rows = self.rank_rows[self.rank]
         self._bufs = {}
+        self._prep1 = None   # (column key, prepared axis-1 launch over a full batch)
+        self._prep0 = {}     # receive buffer -> prepared axis-0 launch
+        self._masks = {}
+        self._ptrs = {}      # output pointer tables of the batched axis-1 launch
         self.launches = 0
         if exchange not in ("auto", "p2p", "nccl"):
             raise ValueError(f"unknown exchange mechanism {exchange!r}")
@@ -220,69 +224,70 @@ class SwiftlyForwardSharded:
             self._bufs[key] = (send.transpose(2, 3), recv.transpose(2, 3), send, recv)
         return self._bufs[key]
 
-    def _local_strips(self, sg, out):
-        """Axis-1 reduction of this rank's facets for subgrid ``sg`` into ``out[row]``."""
-        column = self._column(sg.off0)
-        mask1 = _device_mask(sg.mask1, self.device)
-        groups = [
-            [(column[i], self.facet_configs[i].off1)
-             for i in self.local_idx if self.facet_configs[i].off0 == off0]
-            for off0 in self.my_rows
-        ]
-        if groups:
-            self.core.sum_finish_axis_grouped(
-                groups, out[:len(groups)], axis=1, subgrid_off=sg.off1, mask=mask1)
-            self.launches += 1
+    def _mask(self, sg, axis):
+        off = sg.off0 if axis == 0 else sg.off1
+        key = (axis, off, sg.size)
+        if key not in self._masks:
+            self._masks[key] = _device_mask(sg.mask0 if axis == 0 else sg.mask1, self.device)
+        return self._masks[key]
 
-    def _local_strips_batch(self, batch, out):
-        """Axis-1 reduction for all subgrids of a batch: ``out[b, row]`` for subgrid ``b``.
+    def _batch_launch(self, run, ptrs, like):
+        """ONE axis-1 launch for the subgrids ``run`` (same subgrid column): groups = subgrid x
+        local facet row, group ``(b, row)`` writing to address ``ptrs[b * nrows + row]``.  The
+        argument block (sources of all local facets, for a full batch) is built once per
+        subgrid column; per launch only offsets, masks and output addresses change."""
+        nrows = len(self.my_rows)
+        column = self._column(run[0].off0)
+        key = (id(column), run[0].size)
+        if self._prep1 is None or self._prep1[0] != key:
+            rows = [[(column[i], self.facet_configs[i].off1) for i in self.local_idx
+                     if self.facet_configs[i].off0 == off0] for off0 in self.my_rows]
+            groups = [g for _ in range(self.world) for g in rows]
+            m = self.core.xM_yN_size
+            # a strip is stored transposed: line (row of the contribution) stride 1, sample stride m
+            self._prep1 = (key, self.core.prepare_sum_finish(groups, 1, m, run[0].size, (1, m)),
+                           column)
+        offs = [sg.off1 for sg in run for _ in range(nrows)]
+        masks = [self._mask(sg, 1) for sg in run for _ in range(nrows)]
+        self._prep1[1].launch(offs, masks, out_ptrs=ptrs, stream_of=like,
+                              n_groups=len(run) * nrows)
+        self.launches += 1
 
-        Subgrids that share the subgrid column (``off0``) go into ONE kernel launch (groups =
-        subgrids x local facet rows, per-group subgrid offset and mask)."""
+    def _runs(self, batch):
+        """Maximal runs of consecutive subgrids of a batch that share the subgrid column."""
         b = 0
         while b < len(batch):
-            # the C side cuts a launch that carries more groups / sources than the kernel
-            # parameters hold into several launches, so a run is only bounded by the column
             e = b + 1
             while (e < len(batch) and batch[e].off0 == batch[b].off0
                    and batch[e].size == batch[b].size):
                 e += 1
-            if not self.my_rows:
-                b = e
-                continue
-            run = batch[b:e]
-            nrows = len(self.my_rows)
-            if out[b:e, :nrows].stride(0) != out[b:e, :nrows].stride(1) * nrows:
-                # strips of consecutive subgrids are not evenly spaced (padded rows): per subgrid
-                for k, sg in enumerate(run):
-                    self._local_strips(sg, out[b + k])
-                b = e
-                continue
-            column = self._column(run[0].off0)
-            groups, offs, masks = [], [], []
-            for sg in run:
-                mask1 = _device_mask(sg.mask1, self.device)
-                for off0 in self.my_rows:
-                    groups.append([(column[i], self.facet_configs[i].off1)
-                                   for i in self.local_idx
-                                   if self.facet_configs[i].off0 == off0])
-                    offs.append(sg.off1)
-                    masks.append(mask1)
-            m, xA = out.shape[-2], out.shape[-1]
-            view = out[b:e, :nrows].reshape(len(run) * nrows, m, xA)
-            self.core.sum_finish_axis_grouped(groups, view, axis=1, subgrid_off=offs, mask=masks)
-            self.launches += 1
+            yield b, e
             b = e
+
+    def _local_strips_batch(self, batch, out):
+        """Axis-1 reduction for all subgrids of a batch: ``out[b, row]`` for subgrid ``b``."""
+        if not self.my_rows:
+            return
+        nrows = len(self.my_rows)
+        key = ("nccl", out.data_ptr())
+        if key not in self._ptrs:
+            self._ptrs[key] = [[out[b, k].data_ptr() for k in range(nrows)]
+                               for b in range(out.shape[0])]
+        table = self._ptrs[key]
+        for b, e in self._runs(batch):
+            ptrs = [p for k in range(b, e) for p in table[k]]
+            self._batch_launch(batch[b:e], ptrs, out)
 
     def _finish(self, sg, recv):
         """Axis-0 reduction over the strips of all ranks (owner only)."""
-        sources = []
-        for r in range(self.world):
-            for k, off0 in enumerate(self.rank_rows[r]):
-                sources.append((recv[r, k], off0))
         out = torch.empty((sg.size, sg.size), dtype=torch.complex128, device=self.device)
-        self.core.sum_finish_axis(sources, out, axis=0, subgrid_off=sg.off0,
-                                  mask=_device_mask(sg.mask0, self.device))
+        key = (recv.data_ptr(), sg.size)
+        if key not in self._prep0:
+            sources = [[(recv[r, k], off0) for r in range(self.world)
+                        for k, off0 in enumerate(self.rank_rows[r])]]
+            self._prep0[key] = self.core.prepare_sum_finish(
+                sources, 0, sg.size, sg.size, (out.stride(1), out.stride(0)))
+        self._prep0[key].launch([sg.off0], [self._mask(sg, 0)], out=out)
         self.launches += 1
         return out
 
@@ -344,26 +349,15 @@ class SwiftlyForwardSharded:
         of subgrids that share the subgrid column, every group with its own output buffer."""
         if not self.my_rows:
             return
-        b = 0
-        while b < len(batch):
-            e = b + 1
-            while e < len(batch) and batch[e].off0 == batch[b].off0:
-                e += 1
-            column = self._column(batch[b].off0)
-            groups, offs, masks, outs = [], [], [], []
-            for k in range(b, e):
-                sg = batch[k]
-                mask1 = _device_mask(sg.mask1, self.device)
-                for row, off0 in enumerate(self.my_rows):
-                    groups.append([(column[i], self.facet_configs[i].off1)
-                                   for i in self.local_idx
-                                   if self.facet_configs[i].off0 == off0])
-                    offs.append(sg.off1)
-                    masks.append(mask1)
-                    outs.append(views[k][slot, self.rank, row])
-            self.core.sum_finish_axis_grouped(groups, outs, axis=1, subgrid_off=offs, mask=masks)
-            self.launches += 1
-            b = e
+        nrows = len(self.my_rows)
+        key = ("p2p", slot)
+        if key not in self._ptrs:
+            self._ptrs[key] = [[views[b][slot, self.rank, k].data_ptr() for k in range(nrows)]
+                               for b in range(self.world)]
+        table = self._ptrs[key]
+        for b, e in self._runs(batch):
+            ptrs = [p for k in range(b, e) for p in table[k]]
+            self._batch_launch(batch[b:e], ptrs, views[self.rank])
 
     def _run_p2p(self, batches, xA, consumer, results):
         """Peer-memory exchange, software pipelined.
