@@ -428,8 +428,9 @@ def main():
     ap.add_argument("--selfcheck", action="store_true", help="(default) kept for symmetry")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-cores", type=int, default=0)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="multi-GPU strip exchange: peer-memory stores or NCCL all_to_all")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "copy", "p2p", "nccl"],
+                    help="multi-GPU strip exchange: copy engines on peer memory (auto), TMA "
+                         "stores into peer memory, or NCCL all_to_all")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

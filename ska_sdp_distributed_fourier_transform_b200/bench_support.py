@@ -105,7 +105,7 @@ class ForwardBenchRunner:
         fwd.get_subgrid_tasks(self.sg_cfgs, consumer=consumer or (lambda *a: None))
         # our kernels actually launched by this rank in the step (+ signal / wait per batch)
         nb = -(-len(self.sg_cfgs) // self.world)
-        self.launches_per_step = fwd.launches + (2 * nb if fwd.exchange == "p2p" else 0)
+        self.launches_per_step = fwd.launches + (2 * nb if fwd.exchange in ("p2p", "copy") else 0)
 
     def _barrier(self):
         torch.cuda.synchronize(self.device)

@@ -106,21 +106,21 @@ class SwiftlyForwardSharded:
         self._masks = {}
         self._ptrs = {}      # output pointer tables of the batched axis-1 launch
         self.launches = 0
-        if exchange not in ("auto", "p2p", "nccl"):
+        if exchange not in ("auto", "copy", "p2p", "nccl"):
             raise ValueError(f"unknown exchange mechanism {exchange!r}")
         self.exchange = "nccl"
         self._symm = None
-        if exchange == "p2p" and self.world > 1 and self.device.type == "cuda":
+        self._comm_stream = None
+        want = "copy" if exchange == "auto" else exchange
+        if want in ("p2p", "copy") and self.world > 1 and self.device.type == "cuda":
             try:
                 self._setup_symmetric()
-                self.exchange = "p2p"
+                self.exchange = want
             except Exception as exc:  # pylint: disable=broad-except
-                if exchange == "p2p":
+                if exchange != "auto":
                     raise
                 self._symm = None
                 self.exchange_fallback_reason = f"{type(exc).__name__}: {exc}"
-        elif exchange == "p2p" and self.world == 1:
-            self.exchange = "nccl"
 
     # ------------------------------------------------------------------ symmetric memory
     def _setup_symmetric(self):
@@ -161,6 +161,9 @@ class SwiftlyForwardSharded:
                 peer = hdl.get_buffer(r, (2 * n,), torch.float64, 0)
                 views.append(torch.view_as_complex(peer.view(n, 2)).view(shape).transpose(3, 4))
             st["slots"][xA] = (hdl, views, buf)
+            # untransposed (storage order) views: a rank's part of a slot is one contiguous block
+            st["bases"] = st.get("bases", {})
+            st["bases"][xA] = [v.transpose(3, 4) for v in views]
         return st["slots"][xA]
 
     def _symm_flags(self):
@@ -312,6 +315,8 @@ class SwiftlyForwardSharded:
                    for i in range(0, len(subgrid_configs), self.world)]
         if self.exchange == "p2p":
             return self._run_p2p(batches, xA, consumer, results)
+        if self.exchange == "copy":
+            return self._run_copy(batches, xA, consumer, results)
         pending = None  # (batch index, work, recv buffer)
 
         def finish(bi, work, recv):
@@ -396,6 +401,80 @@ class SwiftlyForwardSharded:
         if bad:
             raise RuntimeError(f"rank {self.rank}: rank {bad - 1} did not deliver its strips "
                                "(peer wait timed out)")
+        return results
+
+
+    def _run_copy(self, batches, xA, consumer, results):
+        """Peer-memory exchange by the COPY ENGINES, software pipelined (``exchange="copy"``).
+
+        The axis-1 kernel writes the strips of a batch into a local send buffer; a communication
+        stream then moves every owner's part into that owner's receive slot with plain
+        device-to-device copies on peer-mapped (symmetric) memory -- NVLink DMA, no SM involved,
+        so the transfer really runs beside the kernels (an NCCL all_to_all needs SMs, which the
+        persistent one-CTA-per-SM kernels of this library do not leave free: measured on 2 GPUs
+        the NCCL exchange serialised with them, 866 ms per step for 625 ms of kernels; scattering
+        the strips straight into peer memory with 16-byte TMA rows is slower still, 921 ms) --
+        and signals the owners (``peer_signal`` on the communication stream).  Compute stream:
+        ``K3(k)``, ``wait(k - 1)``, ``K4(k - 1)``.  Send buffers: two slots, ``K3(k + 2)`` waits
+        for the copies of batch ``k``.  Receive slots: four, as in :meth:`_run_p2p`: my
+        ``signal(k + 2)`` follows my copies of batch ``k + 2``, hence my ``K3(k + 2)``, hence (same
+        stream) my ``K4(k)`` -- so whoever passes ``wait(k + 2)`` may overwrite slot ``k % 4``.
+        """
+        self._symm_slots(xA)
+        bases = self._symm["bases"][xA]   # per rank: (slot, source rank, row, xA, m) storage
+        views = self._symm["slots"][xA][1]
+        _, _, table, my_flags, status = self._symm_flags()
+        base = self._symm["seq"]
+        self._symm["seq"] = base + len(batches)
+        cuda = self.device.type == "cuda"  # (the host-emulated test build runs everything inline)
+        if cuda and self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self.device)
+        comm = self._comm_stream
+        compute = torch.cuda.current_stream(self.device) if cuda else None
+        copied = {}
+
+        def finish(bi):
+            self.core.peer_wait(my_flags, self.world, base + bi + 1, status)
+            batch = batches[bi]
+            if self.rank < len(batch):
+                idx = bi * self.world + self.rank
+                out = self._finish(batch[self.rank], views[self.rank][bi % self.N_SLOTS])
+                if consumer is not None:
+                    consumer(idx, batch[self.rank], out)
+                else:
+                    results[idx] = DeviceTask(out)
+
+        def move(bi, batch, send_flat):
+            slot = bi % self.N_SLOTS
+            for b in range(len(batch)):  # subgrid b of the batch is owned by rank b
+                bases[b][slot, self.rank].copy_(send_flat[b], non_blocking=True)
+            self.core.peer_signal(table, self.world, self.rank, base + bi + 1, my_flags)
+
+        for bi, batch in enumerate(batches):
+            send, _, send_flat, _ = self._buffers(bi % 2, xA)
+            if cuda and bi >= 2:
+                compute.wait_event(copied.pop(bi - 2))
+            self._local_strips_batch(batch, send)
+            if cuda:
+                ready = torch.cuda.Event()
+                ready.record(compute)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ready)
+                    move(bi, batch, send_flat)
+                    done = torch.cuda.Event()
+                    done.record(comm)
+                copied[bi] = done
+            else:
+                move(bi, batch, send_flat)
+            if bi >= 1:
+                finish(bi - 1)
+        finish(len(batches) - 1)
+        bad = int(status.item())
+        if bad:
+            raise RuntimeError(f"rank {self.rank}: rank {bad - 1} did not deliver its strips "
+                               "(peer wait timed out)")
+        if cuda:
+            compute.wait_stream(comm)
         return results
 
 

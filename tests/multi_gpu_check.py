@@ -38,6 +38,8 @@ def main():
         ("n2048-p2p", (13.5625, 2048, 512, 1024, 256, 512), False, "p2p"),
         ("n2048-sparse-p2p", (13.5625, 2048, 512, 1024, 256, 512), True, "p2p"),
         ("n2048-sparse", (13.5625, 2048, 512, 1024, 256, 512), True, "nccl"),
+        ("n2048-copy", (13.5625, 2048, 512, 1024, 256, 512), False, "copy"),
+        ("n2048-sparse-copy", (13.5625, 2048, 512, 1024, 256, 512), True, "copy"),
     ):
         cfg = SwiftlyConfig(W=W, fov=1.0, N=N, yB_size=yB, yN_size=yN, xA_size=xA, xM_size=xM,
                             device=local)
@@ -100,7 +102,7 @@ def main():
         make_subgrid_from_sources)
 
     W, N, yB, yN, xA, xM = 13.5625, 8192, 2048, 4096, 1024, 2048
-    for exchange in ("nccl", "p2p"):
+    for exchange in ("nccl", "p2p", "copy"):
         cfg = SwiftlyConfig(W=W, fov=1.0, N=N, yB_size=yB, yN_size=yN, xA_size=xA, xM_size=xM,
                             device=local)
         facet_cfgs = make_full_facet_cover(cfg)

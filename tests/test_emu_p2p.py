@@ -6,6 +6,7 @@ is exercised without GPUs.  TEST TOOLING -- the real thing runs in tests/multi_g
 """
 
 import numpy
+import pytest
 import torch
 
 from oracle.swiftly_oracle import OracleCore, forward_reference_order
@@ -41,7 +42,8 @@ class _FakeSymm:
         return _FakeHandle(buf)
 
 
-def test_emu_p2p_pipeline_single_rank():
+@pytest.mark.parametrize("mode", ["p2p", "copy"])
+def test_emu_p2p_pipeline_single_rank(mode):
     W, N, yB, yN, xA, xM = 13.5625, 2048, 512, 1024, 256, 512
     core = emu_core_class()(W, N, xM, yN)
     cfg = SwiftlyConfig(W=W, fov=1.0, N=N, yB_size=yB, yN_size=yN, xA_size=xA, xM_size=xM,
@@ -52,7 +54,7 @@ def test_emu_p2p_pipeline_single_rank():
     facets = [pc.rand_c(rng, yB, yB) for _ in offs]
     fwd = SwiftlyForwardSharded(cfg, facet_cfgs, dict(enumerate(facets)), exchange="nccl")
     fwd._symm = {"mod": _FakeSymm, "group": None, "slots": {}}  # pylint: disable=protected-access
-    fwd.exchange = "p2p"
+    fwd.exchange = mode
     sgs = make_full_subgrid_cover(cfg)
     sgs = sgs[:6] + sgs[-1:]  # seven batches of one: every slot is reused
     tasks = fwd.get_subgrid_tasks(sgs)
