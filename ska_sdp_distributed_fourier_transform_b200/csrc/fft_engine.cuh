@@ -64,6 +64,13 @@ struct LastPass {
     static constexpr int ITERS = 16 / R;
 };
 
+// optional hook: sync.pre_store() right before the stores of the LAST pass (e.g. a barrier that
+// orders them after another transform's stores to the same destination)
+template <class S, class = void>
+struct HasPreStore : std::false_type {};
+template <class S>
+struct HasPreStore<S, std::void_t<decltype(std::declval<S&>().pre_store())>> : std::true_type {};
+
 template <class S, class = void>
 struct HasPhaseHooks : std::false_type {};
 template <class S>
@@ -307,6 +314,7 @@ SW_HD void stockham_tail(int lt, double* sm, const cplx* tw, cplx* v, St& st, Sy
         Radix<R, DIR>::run(v + it * R);
     }
     if constexpr (LAST) {
+        if constexpr (HasPreStore<Sync>::value) sync.pre_store();
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const int j = lt + it * T;
@@ -362,6 +370,7 @@ SW_HD void stockham_tail_cx(int lt, cplx* sm, const cplx* tw, cplx* v, St& st, S
         Radix<R, DIR>::run(v + it * R);
     }
     if constexpr (LAST) {
+        if constexpr (HasPreStore<Sync>::value) sync.pre_store();
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const int j = lt + it * T;

@@ -100,6 +100,15 @@ struct SubgridAxisKernelPP {
         // cycles, the time 2 x 64 KiB need at an SM's fair share of the HBM bandwidth)
         const void* pf_ptr[2];
         uint32_t pf_bytes[2];
+        // the accumulator update of a later round must come after ALL transforms of the
+        // earlier rounds have stored (their windows overlap): one group barrier right before
+        // the stores, instead of one after every round -- the concurrent transforms of a line
+        // run on through the round boundary and drift apart, so that their load, exchange and
+        // butterfly phases overlap instead of hitting the same pipe at the same moment
+        bool order_stores;
+        SW_HD void pre_store() const {
+            if (order_stores) ctx.group_sync(1 + grp, T_X);
+        }
         SW_HD void operator()() const { ctx.group_sync(bar_id, bar_count); }
         // start of an exchange phase: with TOKENS wait for the token (the other group's
         // release); either way a barrier over (at least) the transform's threads
@@ -135,9 +144,10 @@ struct SubgridAxisKernelPP {
         double* work = (double*)((cplx*)ctx.smem + (size_t)GROUPS * ACCS) + (size_t)grp * WORK;
         const int c = t / T_M;
         const int lt = t % T_M;
-        GroupSync<Ctx> gsync{ctx, 1 + grp, T_X, grp, t, false, {nullptr, nullptr}, {0, 0}};
+        GroupSync<Ctx> gsync{ctx, 1 + grp, T_X, grp, t, false, {nullptr, nullptr}, {0, 0}, false};
         GroupSync<Ctx> msync{ctx, SUB_BARRIERS ? 3 + grp * CONC + c : 1 + grp,
-                             SUB_BARRIERS ? T_M : T_X, grp, t, false, {nullptr, nullptr}, {0, 0}};
+                             SUB_BARRIERS ? T_M : T_X, grp, t, false, {nullptr, nullptr}, {0, 0},
+                             false};
         // group 1 hands the token to group 0 to start with
         if (TOKENS && grp == 1) ctx.group_arrive(11, THREADS);
         const int64_t pairs = (n_lines + GROUPS - 1) / GROUPS;  // line pairs per source group
@@ -220,9 +230,10 @@ struct SubgridAxisKernelPP {
                         }
                     }
                 }
+                msync.order_stores = slot0 > 0;
                 line_fft<M, -1>(lt, work + (size_t)c * WSTRIDE, tw_m, ld, st, msync);
-                gsync();  // accumulator complete; work buffers free
             }
+            gsync();  // accumulator complete
             {
                 cplx* o = (out_g[sgrp] ? out_g[sgrp] : out + (int64_t)sgrp * out_gs) + line * out_ls;
                 const int gstart = start[sgrp];
