@@ -172,7 +172,9 @@ def cpu_facets_per_step(params, cores):
     """Facets of the column slice one CPU step runs (bounds a step to a few seconds)."""
     N, yB = params["N"], params["yB_size"]
     F = (-(-N // yB)) ** 2
-    return max(1, min(F, cores))
+    # half a facet per core: a cfg4 step then takes ~8 s on 16 cores, so that the driver's
+    # --steps 20 run of the reference arm stays within a few minutes
+    return max(1, min(F, max(4, cores // 2)))
 
 
 def cpu_baseline_entry(params, cores, steps=1, warmup=0):

@@ -133,6 +133,8 @@ struct DeviceCtx {
     __device__ __forceinline__ void group_arrive(int id, int count) const {
         asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
     }
+    // let the calling thread sleep for about `ns` nanoseconds
+    __device__ __forceinline__ void nap(unsigned ns) const { __nanosleep(ns); }
     // ---- bulk asynchronous copies (TMA engine, cp.async.bulk) tracked by an mbarrier ----
     // `bar` is an 8-byte shared-memory word; one thread initialises it (count 1 = the thread
     // that issues the copies), everybody waits on its phase parity.

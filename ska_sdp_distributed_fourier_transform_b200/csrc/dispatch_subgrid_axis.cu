@@ -66,6 +66,7 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
     k.tma_slot_line = k.tma_slot_elem = k.tma_slot_group = 1;
     k.tma_per_group = a.out_g[0] != nullptr ? 1 : 0;
     k.pf_mode = h->sg_variant == 11 ? 1 : (h->sg_variant == 12 ? 2 : 0);
+    k.stagger_ns = h->sg_variant == 13 ? 5000 : (h->sg_variant == 14 ? 2500 : 0);
     // (the last box may be partial: the engine still reads a whole box from shared memory)
     const size_t staged = (size_t)((a.sz + k.tma_box - 1) / (k.tma_box > 0 ? k.tma_box : 1)) *
                           (size_t)k.tma_box * sizeof(cplx);

@@ -74,6 +74,7 @@ struct SubgridAxisKernelPP {
     int tma_box;                                       // samples per bulk tensor store
     int tma_slot_line, tma_slot_elem, tma_slot_group;  // coordinate slots (1..3)
     int tma_per_group;                 // one tensor map per group (groups in different buffers)
+    int stagger_ns;                    // group 1 starts this much later than group 0 (see below)
     int pf_mode;                       // L2 prefetch: 0 bulk at the first exchange (default),
                                        // 1 none, 2 per-thread prefetch at the start of the round
     cplx* out_g[SW_MAX_GROUPS];        // optional per-group output base (null: out + g * out_gs)
@@ -150,6 +151,13 @@ struct SubgridAxisKernelPP {
                              false};
         // group 1 hands the token to group 0 to start with
         if (TOKENS && grp == 1) ctx.group_arrive(11, THREADS);
+        // The two groups run identical work and would stay in step: both waiting for their
+        // windows at the same time, both in the lockstep xM transform at the same time.  Group 1
+        // starts about half a line late, so that one group's load / xM phases fall into the
+        // other group's m-point rounds.
+        if (grp == 1 && stagger_ns > 0) {
+            for (int left = stagger_ns; left > 0; left -= 1000) ctx.nap(1000);
+        }
         const int64_t pairs = (n_lines + GROUPS - 1) / GROUPS;  // line pairs per source group
         const int64_t total = pairs * n_groups;
         for (int64_t gl = ctx.bid; gl < total; gl += ctx.nblocks) {

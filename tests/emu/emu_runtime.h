@@ -98,6 +98,7 @@ struct HostCtx {
     }
     inline void tx_wait(uint64_t*, uint32_t) const {}
     inline void bulk_prefetch_l2(const void*, uint32_t) const {}
+    inline void nap(unsigned) const {}
     inline void fence_async() const {}
     inline void bulk_commit() const {}
     inline void bulk_wait_read() const {}

@@ -95,6 +95,7 @@ int main() {
     k.start[0] = 1024;
     k.scale = 1.0 / XM;
     k.first_round_tiles = 1;
+    k.stagger_ns = 0;
     long long* log;
     int* counts;
     cudaMalloc(&log, sizeof(long long) * grid * MAXEV);
