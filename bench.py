@@ -168,31 +168,41 @@ class ClockSampler:
 
 
 # ====================================================================== CPU arm
-def cpu_facets_per_step(params, cores):
-    """Facets of the column slice one CPU step runs (bounds a step to a few seconds)."""
-    N, yB = params["N"], params["yB_size"]
-    F = (-(-N // yB)) ** 2
-    # half a facet per core: a cfg4 step then takes ~8 s on 16 cores, so that the driver's
-    # --steps 20 run of the reference arm stays within a few minutes
-    return max(1, min(F, max(4, cores // 2)))
-
-
-def cpu_baseline_entry(params, cores, steps=1, warmup=0):
+def cpu_baseline_entry(params, cores, steps=1, warmup=0, budget_s=200.0):
     """The reference algorithm RUNNING on the host cores (oracle/cpu_arm.py): one timed
     subgrid column of the forward transform per step -- real shapes, reference task order,
-    all cores -- no unit-cost model."""
+    all cores -- no unit-cost model.
+
+    A step normally covers ``cores`` facets (one facet task per core).  When the caller asks for
+    so many steps that this would take longer than ``budget_s`` in total, the first (warm-up)
+    step measures the cost per contribution and the timed steps use fewer facets, each split
+    into row blocks so that every core still has work; what was run is stated in ``sample``.
+    """
     from oracle.cpu_arm import run_column_slice
 
-    nf = cpu_facets_per_step(params, cores)
-    for _ in range(warmup):
-        run_column_slice(params, cores, max_facets=nf)
-    runs = [run_column_slice(params, cores, max_facets=nf) for _ in range(max(1, steps))]
+    N, yB = params["N"], params["yB_size"]
+    F = (-(-N // yB)) ** 2
+    nf = max(1, min(F, cores))
+    chunks = 1
+    probe = None
+    if warmup > 0 or steps > 1:
+        probe = run_column_slice(params, cores, max_facets=nf)
+        need = probe["wall_s"] * max(1, steps)
+        if need > budget_s:
+            nf = max(2, min(nf, int(nf * budget_s / need)))
+            chunks = -(-cores // nf)
+    runs = [run_column_slice(params, cores, max_facets=nf, chunks=chunks)
+            for _ in range(max(1, steps))]
     rate = float(numpy.mean([r["rate"] for r in runs]))
     last = runs[-1]
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": last["kind"],
-            "sample": last["sample"], "steps": len(runs),
-            "step_wall_s": [r["wall_s"] for r in runs],
-            "phase_a_s": last["phase_a_s"], "phase_b_s": last["phase_b_s"]}
+    entry = {"value": rate, "unit": UNIT, "cores": cores, "kind": last["kind"],
+             "sample": last["sample"], "steps": len(runs),
+             "step_wall_s": [r["wall_s"] for r in runs],
+             "phase_a_s": last["phase_a_s"], "phase_b_s": last["phase_b_s"]}
+    if probe is not None:
+        entry["full_size_probe"] = {"rate": probe["rate"], "wall_s": probe["wall_s"],
+                                    "contributions": probe["contributions"]}
+    return entry
 
 
 def main_reference(args):

@@ -146,14 +146,26 @@ def _shared(shape):
     return numpy.frombuffer(buf, dtype=numpy.complex128, count=n).reshape(shape)
 
 
-def _phase_a(j):
+def _phase_a(task):
+    """One facet's share of the column -- or, when there are fewer facets than cores, one of
+    ``chunks`` row blocks of it (the lines of both stages are independent; the reference's
+    task is the whole facet, smaller tasks only help the CPU)."""
+    j, c = task
     g = _G
     impl, fc = g["impl"], g["facet_cfgs"][j]
-    rng = numpy.random.default_rng(123456789 + j)
-    yB, slab = g["yB"], g["slab"]
+    chunks = g["chunks"]
+    rng = numpy.random.default_rng(123456789 + j * 64 + c)
+    yB = g["yB"]
+    slab = max(1, g["slab"] // chunks)
     facet_slab = rng.standard_normal((yB, slab)) + 1j * rng.standard_normal((yB, slab))
     impl.core.prepare_facet(facet_slab, fc.off0, axis=0)  # this column's share of stage 1
-    g["nmbf"][j][:] = impl.extract_column(g["bf_f"], g["sg_off0"], fc.off1)
+    if chunks == 1:
+        g["nmbf"][j][:] = impl.extract_column(g["bf_f"], g["sg_off0"], fc.off1)
+        return j
+    m = g["nmbf"][j].shape[0]
+    r0, r1 = c * m // chunks, (c + 1) * m // chunks
+    rows = impl.core.extract_from_facet(g["bf_f"], g["sg_off0"], axis=0)[r0:r1]
+    g["nmbf"][j][r0:r1] = impl.core.prepare_facet(rows, fc.off1, axis=1)
     return j
 
 
@@ -166,7 +178,7 @@ def _phase_b(i):
     return float(numpy.abs(out).max())
 
 
-def run_column_slice(params, cores, max_facets=None):
+def run_column_slice(params, cores, max_facets=None, chunks=1):
     """Time one subgrid column of the forward transform on ``cores`` worker processes.
 
     Returns a dict with ``rate`` (contributions / s), ``contributions``, ``wall_s``, the phase
@@ -192,13 +204,14 @@ def run_column_slice(params, cores, max_facets=None):
     bf_f.real[:] = rng.standard_normal((yN, yB))
     bf_f.imag[:] = 0.5
     nmbf = [_shared((m, yN)) for _ in range(F)]
+    chunks = max(1, int(chunks))
     _G.update(impl=impl, facet_cfgs=facet_cfgs, sg_cfgs=sg_cfgs, yB=yB, slab=slab, bf_f=bf_f,
-              nmbf=nmbf, sg_off0=sg_cfgs[0].off0)
+              nmbf=nmbf, sg_off0=sg_cfgs[0].off0, chunks=chunks)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         pool.map(_phase_b, [])  # workers are up before the clock starts
         t0 = time.perf_counter()
-        pool.map(_phase_a, range(F), chunksize=1)
+        pool.map(_phase_a, [(j, c) for j in range(F) for c in range(chunks)], chunksize=1)
         t1 = time.perf_counter()
         peaks = pool.map(_phase_b, range(len(sg_cfgs)), chunksize=1)
         t2 = time.perf_counter()
@@ -212,7 +225,8 @@ def run_column_slice(params, cores, max_facets=None):
         "sample": (f"one subgrid column ({len(sg_cfgs)} of {len(all_sgs)} subgrids) of the "
                    f"forward transform for {F} facets, real shapes, reference task order, on "
                    f"{cores} worker processes: per facet prepare_facet(axis 0) on its "
-                   f"{slab}-column share of the facet + extract_column at full size, then per "
+                   f"{slab}-column share of the facet + extract_column at full size"
+                   + (f" (in {chunks} row blocks)" if chunks > 1 else "") + ", then per "
                    f"subgrid {F} contributions + sum_and_finish_subgrid; {count} contributions "
                    f"in {wall:.1f} s wall"),
     }

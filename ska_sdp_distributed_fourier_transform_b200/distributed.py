@@ -17,22 +17,24 @@ move and without replicating the axis-0 work.  The exchange of batch ``k`` runs 
 the communication stream while the compute stream produces the strips of batch
 ``k + 1`` and finishes the subgrids of batch ``k - 1``.
 
-Two exchange mechanisms:
+Three exchange mechanisms (all parity-checked on 2 and 4 B200, ``tests/multi_gpu_check.py``):
 
-* ``exchange="p2p"``: the receive buffers are
-  allocated as *symmetric memory* (``torch.distributed._symmetric_memory``), every rank maps
-  its peers' buffers, and the axis-1 kernel of subgrid ``b`` stores its strips DIRECTLY into
-  the owner's buffer over NVLink -- the transfer is the kernel's own epilogue, tile by tile,
-  there is no separate collective and no staging copy.  One device-side barrier per batch
-  orders "all strips written" before the owners' axis-0 kernels; with two buffer slots the
-  same barrier also protects the re-use of a slot two batches later.
-* ``exchange="nccl"`` (what ``"auto"`` selects): strips are written locally and moved by one
-  ``all_to_all`` per batch on the communication stream, overlapped with the compute stream
-  (double buffered).  This is also the path the CPU (gloo) tests exercise.
+* ``exchange="copy"`` (what ``"auto"`` selects): the axis-1 kernel writes the strips of a batch
+  into a local send buffer, a communication stream moves every owner's part into that owner's
+  receive slot -- symmetric memory (``torch.distributed._symmetric_memory``), every rank maps
+  its peers' slots -- with plain device-to-device copies: NVLink DMA by the copy engines, no SM
+  involved, so the transfer really runs beside the kernels; ordering by device-side flags
+  (``peer_signal`` / ``peer_wait``, ``csrc/peer_sync.cu``), software pipelined by one batch.
+* ``exchange="p2p"``: the axis-1 kernel of a batch stores its strips DIRECTLY into the owners'
+  slots over NVLink -- bulk tensor stores of the TMA engine on peer-mapped addresses, the transfer
+  is the kernel's own epilogue, no copy and no collective; same flags and pipeline.
+* ``exchange="nccl"``: one ``all_to_all`` per batch on the communication stream, double
+  buffered.  This is also the path the CPU (gloo) tests exercise.
 
-Measured at cfg4 on 2 B200 (round 1): nccl 791 ms/step, p2p 907 ms/step (both parity-green) --
-the p2p path runs everything on one stream with a blocking barrier per batch, the NCCL path
-hides the exchange behind the next batch, so ``"auto"`` currently means NCCL.
+Measured at cfg4 on 2 B200 (round 2, 625 ms of kernels per step): copy 639 ms, nccl 866 ms, p2p
+921 ms.  The NCCL kernels need SMs, which the persistent one-CTA-per-SM kernels of this library
+(up to 209 KiB of shared memory) do not leave free, so the collective serialises with them; the
+16-byte rows of the transposed strips make poor NVLink packets for the TMA variant.
 
 Calls are collective (SPMD): every rank must call ``get_subgrid_tasks`` with the same
 subgrid list.
