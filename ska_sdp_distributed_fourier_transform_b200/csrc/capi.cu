@@ -370,6 +370,7 @@ static int prepare_facet_impl(const swiftly_b200* h, const swiftly_b200_lines* i
             a.fs = (int)fs;
             a.shift_in = (int)pmod(fs / 2 - facet_off, yN);
             a.ncols = (int)nc;
+            a.lw = lw ? lw + c0 : nullptr;
             SW_TRY(run_prepare_facet_pass_a(h, a, s));
             PrepareFacetPassBOp b;
             b.g = g;
@@ -381,7 +382,6 @@ static int prepare_facet_impl(const swiftly_b200* h, const swiftly_b200_lines* i
             b.n2 = n2;
             b.ncols = (int)nc;
             b.scale = 1.0 / (double)yN;
-            b.lw = lw ? lw + c0 : nullptr;
             SW_TRY(run_prepare_facet_pass_b(h, b, s));
         }
         return stage_out(sout, s);

@@ -59,10 +59,9 @@ static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op,
 }
 
 // 4 x Q split with two thread groups (extract_tma.cuh)
-template <int Q>
+template <int Q, class K>
 static int launch_extract_tma4(const swiftly_b200* h, const ExtractColumnsOp& op, int max_fs,
-                               cudaStream_t s) {
-    typedef ExtractColumnsTma4Kernel<Q> K;
+                               cudaStream_t s, int scratch_lines) {
     K k;
     static thread_local typename K::Maps maps;
     k.op = op;
@@ -100,7 +99,7 @@ static int launch_extract_tma4(const swiftly_b200* h, const ExtractColumnsOp& op
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)148 * per_sm;
     if (blocks > op.g.n_lines) blocks = op.g.n_lines;
-    k.scratch = split_scratch(h, s, (size_t)blocks * 4 * Q);
+    k.scratch = split_scratch(h, s, (size_t)blocks * scratch_lines * Q);
     if (!k.scratch) return SWIFTLY_B200_ECUDA;
     cudaError_t e = launch_body_maps(k, maps, (int)blocks, smem, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK
@@ -127,13 +126,23 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
         if (h->sg_variant != 7 && h->force_split != 1) {
             switch (n) {
                 case 16384: {
-                    int rc = launch_extract_tma4<4096>(h, op, max_fs, s);
+                    // sg_variant 15: the 4 x Q form with a CTA-wide combine (measured equal to
+                    // 2 x 2Q); default: two fully independent groups (DIF across, DIT within)
+                    int rc = h->sg_variant == 15
+                        ? launch_extract_tma4<4096, ExtractColumnsTma4Kernel<4096>>(h, op, max_fs, s, 4)
+                        : (max_fs <= n / 2
+                           ? launch_extract_tma4<4096, ExtractColumnsTmaDifKernel<4096, false>>(h, op, max_fs, s, 2)
+                           : launch_extract_tma4<4096, ExtractColumnsTmaDifKernel<4096, true>>(h, op, max_fs, s, 2));
                     if (rc != -1) return rc;
                     break;
                 }
 #if defined(SWIFTLY_EMU)
                 case 512: {
-                    int rc = launch_extract_tma4<128>(h, op, max_fs, s);
+                    int rc = h->force_split == 3
+                        ? launch_extract_tma4<128, ExtractColumnsTma4Kernel<128>>(h, op, max_fs, s, 4)
+                        : (max_fs <= n / 2
+                           ? launch_extract_tma4<128, ExtractColumnsTmaDifKernel<128, false>>(h, op, max_fs, s, 2)
+                           : launch_extract_tma4<128, ExtractColumnsTmaDifKernel<128, true>>(h, op, max_fs, s, 2));
                     if (rc != -1) return rc;
                     break;
                 }

@@ -360,4 +360,235 @@ struct ExtractColumnsTma4Kernel {
     }
 };
 
+// ---------------------------------------------------------------------------------------
+// yN = 4 Q, two FULLY independent thread groups: decimation in frequency by two ACROSS the
+// groups, decimation in time by two WITHIN a group.
+//
+//   group g (0: even outputs, 1: odd outputs):   y_g[j] = (z[j] + (-1)^g z[j + 2Q]) w^(g j),
+//       j < 2Q, w = exp(+2 pi i / yN);  X[2 k + g] = FFT_2Q(y_g)[k]
+//   inside the group:  E0 = FFT_Q(y_g[2 j]),  E1 = FFT_Q(y_g[2 j + 1]),  v = exp(+2 pi i / 2Q)
+//       FFT_2Q(y_g)[k] = E0[k] + v^k E1[k],   FFT_2Q(y_g)[k + Q] = E0[k] - v^k E1[k]
+//
+// For facets of at most yN/2 samples only one of z[j], z[j + 2Q] is non-zero: both groups
+// transform the SAME staged row, group 1 with a twiddle at load time (by recurrence).  Unlike
+// the 4 x Q form above there is no CTA-wide combine phase, no CTA barrier inside a line and
+// half the scratch traffic (each group parks only its own E0): the groups meet only at the
+// staging buffer (mbarrier wait at the top of a line, the second group past its last
+// first-pass load refills it).  The price: every group stores 16-byte samples at a 32-byte
+// stride (the other group fills the gaps; the sectors merge in L2).
+// BOTH: facets longer than yN/2 exist, z[j] and z[j + 2Q] may both be non-zero (two reads per
+// sample; the common fs <= yN/2 case reads one).
+template <int Q, bool BOTH>
+struct ExtractColumnsTmaDifKernel {
+    static constexpr int DIR = +1;
+    static constexpr int TG = FftCfg<Q>::T;
+    static constexpr int THREADS = 2 * TG;
+    static constexpr int H = 2 * Q;
+    static constexpr int N = 4 * Q;
+    static constexpr int XBUF = (FftCfg<Q>::PADDED + 1) & ~1;
+    static constexpr size_t smem_bytes(int in_cap) {
+        return (size_t)in_cap * sizeof(cplx) + 2 * (size_t)XBUF * sizeof(double) + 32;
+    }
+
+    ExtractColumnsOp op;
+    const cplx* tw;   // compact table of the Q-point plan
+    const cplx* twf;  // exp(-2 pi i t / yN), t < yN / 2
+    cplx* scratch;    // gridDim.x * 2 Q samples (E0 of both groups)
+    int in_cap;
+    int swizzled;
+    int box_chunks;
+    struct Maps {
+        TensorMap4 in_map[SW_MAX_COLUMN_FACETS];
+    };
+
+    SW_HD cplx root(int t) const {  // exp(DIR 2 pi i t / N), 0 <= t < N
+        const bool neg = t >= N / 2;
+        cplx w = ldg_c(twf + (neg ? t - N / 2 : t));
+        if (DIR > 0) w.y = -w.y;
+        return neg ? mk(-w.x, -w.y) : w;
+    }
+
+    template <class Ctx>
+    SW_HD void issue(const Ctx& ctx, cplx* in, uint64_t* bar, int64_t line) const {
+        const int f = (int)(line / op.lines_per);
+        const int l = (int)(line - (int64_t)f * op.lines_per);
+        const ColumnFacet& F = op.fac[f];
+        const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
+        if (swizzled) {
+            const int chunks = F.fs / 8;
+            const int boxes = (chunks + box_chunks - 1) / box_chunks;
+            ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
+            for (int c0 = 0; c0 < chunks; c0 += box_chunks)
+                ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
+                                (int)row, bar);
+            return;
+        }
+        const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
+        ctx.tx_expect(bar, bytes);
+        const char* src = (const char*)(F.in + row * F.in_ls);
+        for (uint32_t o = 0; o < bytes; o += 65536u)
+            ctx.tx_copy((char*)in + o, src + o, bytes - o < 65536u ? bytes - o : 65536u, bar);
+    }
+
+    template <class Ctx>
+    struct GroupSync {
+        const Ctx& ctx;
+        const ExtractColumnsTmaDifKernel& k;
+        int grp, tg;
+        cplx* in;
+        uint64_t* bar;
+        int* done;
+        int64_t next_line;
+        bool pending;
+        SW_HD void operator()() {
+            ctx.group_sync(1 + grp, TG);
+            if (pending) {
+                pending = false;
+                if (tg == 0) {
+#if defined(__CUDA_ARCH__)
+                    const int prev = atomicAdd(done, 1);
+#else
+                    const int prev = (*done)++;
+#endif
+                    if ((prev & 1) == 1 && next_line < k.op.g.n_lines)
+                        k.issue(ctx, in, bar, next_line);
+                }
+            }
+        }
+    };
+
+    template <class Ctx>
+    SW_HD void operator()(Ctx& ctx) const {
+        cplx* in = (cplx*)ctx.smem;
+        double* xb = (double*)(in + in_cap);
+        uint64_t* bar = (uint64_t*)(xb + 2 * XBUF);
+        int* done = (int*)(bar + 1);
+        const int grp = ctx.tid / TG;
+        const int tg = ctx.tid % TG;
+        double* sm = xb + (size_t)grp * XBUF;
+        cplx* stash = scratch + ((size_t)ctx.bid * 2 + grp) * Q;
+        const int n = op.n;
+        if (ctx.tid == 0) {
+            ctx.tx_init(bar);
+            *done = 0;
+            if ((int64_t)ctx.bid < op.g.n_lines) issue(ctx, in, bar, ctx.bid);
+        }
+        ctx.sync();
+        uint32_t parity = 0;
+        typedef LastPass<Q> LP;
+        for (int64_t line = ctx.bid; line < op.g.n_lines; line += ctx.nblocks) {
+            const int f = (int)(line / op.lines_per);
+            const int l = (int)(line - (int64_t)f * op.lines_per);
+            const ColumnFacet& F = op.fac[f];
+            const int shift_in = F.shift_in, fs = F.fs;
+            const double* fb = op.fb ? op.fb + F.fb_off : nullptr;
+            cplx* o = F.out + (int64_t)l * F.out_ls;
+            const double scale = op.scale;
+            const bool swz = swizzled != 0;
+            auto sample = [&](int q) {  // natural-order sample q of the padded, rotated row
+                int k = wrap_add(q, shift_in, n);
+                if (k >= fs) return mk(0.0, 0.0);
+                const int ks = swz ? ((k & ~7) | ((k ^ (k >> 3)) & 7)) : k;
+                return fb ? cscale(in[ks], ldg_d(fb + k)) : in[ks];
+            };
+            ctx.tx_wait(bar, parity);
+            parity ^= 1;
+            GroupSync<Ctx> gs{ctx, *this, grp, tg, in, bar, done, line + ctx.nblocks, false};
+            // sub-transform `half` of the group's sequence: y_g[2 j + half], j = tg + r * NB
+            {
+                constexpr int half = 0;
+                // group 1's load twiddle w^(2 j + half): four table loads per thread (r = 0, 4, 8,
+                // 12), the samples in between by three multiplications with the step w^(2 NB)
+                const cplx w_step = root((2 * (Q / 16)) % N);
+                cplx w_ld = mk(1.0, 0.0);
+                int calls = 0;
+                auto ld = [&](int j) {
+                    const int q = 2 * j + half;
+                    cplx y;
+                    if constexpr (BOTH) {
+                        cplx a = sample(q), b = sample(q + H);
+                        y = grp ? csub(a, b) : cadd(a, b);
+                    } else {
+                        // fs <= 2Q: at most one of the two is inside the facet
+                        int k = wrap_add(q, shift_in, n);
+                        const bool second = k >= fs;
+                        if (second) k = wrap_add(k, H, n);
+                        if (k >= fs) {
+                            y = mk(0.0, 0.0);
+                        } else {
+                            const int ks = swz ? ((k & ~7) | ((k ^ (k >> 3)) & 7)) : k;
+                            y = fb ? cscale(in[ks], ldg_d(fb + k)) : in[ks];
+                            if (second && grp) y = mk(-y.x, -y.y);
+                        }
+                    }
+                    if (grp) {
+                        w_ld = (calls & 3) == 0 ? root(q % N) : cmul(w_ld, w_step);
+                        y = cmul(y, w_ld);
+                    }
+                    ++calls;
+                    return y;
+                };
+                auto st = [&](int k, cplx v) { stash[k] = v; };
+                line_fft<Q, DIR>(tg, sm, tw, ld, st, gs);
+                gs();  // the group's exchange buffer is reused by its second sub-transform
+            }
+            {
+                constexpr int half = 1;
+                // group 1's load twiddle w^(2 j + half): four table loads per thread (r = 0, 4, 8,
+                // 12), the samples in between by three multiplications with the step w^(2 NB)
+                const cplx w_step = root((2 * (Q / 16)) % N);
+                cplx w_ld = mk(1.0, 0.0);
+                int calls = 0;
+                auto ld = [&](int j) {
+                    const int q = 2 * j + half;
+                    cplx y;
+                    if constexpr (BOTH) {
+                        cplx a = sample(q), b = sample(q + H);
+                        y = grp ? csub(a, b) : cadd(a, b);
+                    } else {
+                        // fs <= 2Q: at most one of the two is inside the facet
+                        int k = wrap_add(q, shift_in, n);
+                        const bool second = k >= fs;
+                        if (second) k = wrap_add(k, H, n);
+                        if (k >= fs) {
+                            y = mk(0.0, 0.0);
+                        } else {
+                            const int ks = swz ? ((k & ~7) | ((k ^ (k >> 3)) & 7)) : k;
+                            y = fb ? cscale(in[ks], ldg_d(fb + k)) : in[ks];
+                            if (second && grp) y = mk(-y.x, -y.y);
+                        }
+                    }
+                    if (grp) {
+                        w_ld = (calls & 3) == 0 ? root(q % N) : cmul(w_ld, w_step);
+                        y = cmul(y, w_ld);
+                    }
+                    ++calls;
+                    return y;
+                };
+                // v^k = exp(DIR 2 pi i k / 2Q) = root(2 k) by recurrence over the outputs
+                const cplx v_it = root((2 * TG) % N), v_r = root((2 * LP::NS) % N);
+                cplx w_it = mk(1.0, 0.0), w = mk(1.0, 0.0);
+                auto st = [&](int k, cplx od, int it, int r) {
+                    if (r == 0) {
+                        w_it = it == 0 ? root((2 * k) % N) : cmul(w_it, v_it);
+                        w = w_it;
+                    } else {
+                        w = cmul(w, v_r);
+                    }
+                    const cplx e = stash[k];
+                    const cplx wo = cmul(od, w);
+                    // FFT_2Q(y_g)[k] -> X[2 k + g],  FFT_2Q(y_g)[k + Q] -> X[2 (k + Q) + g]
+                    int pc = wrap_add(2 * k + grp, n / 2, n);
+                    st_stream(o + pc, cscale(cadd(e, wo), scale));
+                    pc = wrap_add(2 * (k + Q) + grp, n / 2, n);
+                    st_stream(o + pc, cscale(csub(e, wo), scale));
+                };
+                gs.pending = true;
+                line_fft<Q, DIR>(tg, sm, tw, ld, st, gs);
+                gs();  // exchange buffer / scratch line are reused by the group's next line
+            }
+        }
+    }
+};
+
 }  // namespace swiftly

@@ -86,12 +86,17 @@ struct PrepareFacetPassAOp {
     const double* fb;
     const cplx* twf;  // exp(-2 pi i t / n), t < n/2
     int n, n1, n2, fs, shift_in, ncols;
+    const double* lw;  // optional per-column weights (see PrepareFacetOp::lw): the transform is
+                       // linear, so the weight of column c is applied to its INPUT samples --
+                       // one table value per line instead of one per stored sample
     SW_HD cplx load(int64_t line, int q) const {
         const int j2 = (int)(line / ncols);
         const int c = (int)(line - (int64_t)j2 * ncols);
         int k = wrap_add(q * n2 + j2, shift_in, n);
         if (k >= fs) return mk(0.0, 0.0);
-        return cscale(ld_stream(g.in + (int64_t)k * g.in_es + c), ldg_d(fb + k));
+        double f = ldg_d(fb + k);
+        if (lw) f *= ldg_d(lw + c);
+        return cscale(ld_stream(g.in + (int64_t)k * g.in_es + c), f);
     }
     // The inter-pass twiddles w^(j2 k1) of a thread's outputs k1 = j0 + it * T + r * NS follow
     // by recurrence from three table values that depend on (j2, thread) only: prep() loads them
@@ -129,7 +134,6 @@ struct PrepareFacetPassBOp {
     Lines g;  // g.in: scratch T; g.out: prepared facet (n rows, row stride out_es)
     int n, n1, n2, ncols;
     double scale;
-    const double* lw;  // optional per-column weights (see PrepareFacetOp::lw)
     SW_HD cplx load(int64_t line, int q) const {
         const int k1 = (int)(line / ncols);
         const int c = (int)(line - (int64_t)k1 * ncols);
@@ -139,8 +143,7 @@ struct PrepareFacetPassBOp {
         const int k1 = (int)(line / ncols);
         const int c = (int)(line - (int64_t)k1 * ncols);
         int pc = wrap_add(k1 + n1 * k2, n / 2, n);
-        const double f = lw ? scale * ldg_d(lw + c) : scale;
-        st_stream(g.out + (int64_t)pc * g.out_es + c, cscale(v, f));
+        st_stream(g.out + (int64_t)pc * g.out_es + c, cscale(v, scale));
     }
 };
 

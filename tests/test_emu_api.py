@@ -53,11 +53,12 @@ def test_emu_forward_backward_vs_oracle_kernel_variants(sg_variant):
     api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)
 
 
-@pytest.mark.parametrize("force_split", [1, 2])
+@pytest.mark.parametrize("force_split", [1, 2, 3])
 def test_emu_forward_split_k2_kernels(force_split):
     """K2 through the split kernels that serve yN = 16384 on the GPU, forced at yN = 512:
-    1 = 2 x 256 (one thread group, E parked in the scratch), 2 = 4 x 128 (two thread groups on
-    the same TMA-staged, swizzled row)."""
+    1 = 2 x 256 (one thread group, E parked in the scratch), 2 = two independent thread groups
+    (DIF across the groups, DIT within) on the same TMA-staged, swizzled row, 3 = 4 x 128 with a
+    CTA-wide combine."""
     import numpy
 
     from oracle.swiftly_oracle import OracleCore, forward_reference_order

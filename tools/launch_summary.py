@@ -17,7 +17,7 @@ for r in rd:
     val = float(r["Metric Value"].replace(",", ""))
     unit = r["Metric Unit"]
     scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)
-    m = re.search(r"kernel_entry<swiftly::(\w+)<([^>]*)", name)
+    m = re.search(r"kernel_entry(?:_maps)?<(?:swiftly::)?(\w+)<([^>]*)", name)
     key = f"{m.group(1)}<{m.group(2)}>" if m else name.split("(")[0][:60]
     tot[key][0] += 1
     tot[key][1] += val * scale
