@@ -62,6 +62,9 @@ int swiftly_b200_create(double W, int64_t N, int64_t xM_size, int64_t yN_size,
                         const double* Fb, const double* Fn, int device, swiftly_b200** plan);
 void swiftly_b200_destroy(swiftly_b200* plan);
 const char* swiftly_b200_last_error(void);
+/* Free the plan's per-stream scratch buffers (up to 2 GiB after prepare_facet along the strided
+ * axis at N = 65536); they are re-created on demand.  Synchronises the owning streams. */
+void swiftly_b200_release_scratch(swiftly_b200* plan);
 /* Library identification: "swiftly_b200 <version> cuda sm_100a" (or "... EMULATED" for
  * the test-only host build, which the product never loads). */
 const char* swiftly_b200_build_info(void);

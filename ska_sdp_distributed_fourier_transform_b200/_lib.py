@@ -63,6 +63,7 @@ SYMBOLS = {
     "swiftly_b200_last_error": (ctypes.c_char_p, []),
     "swiftly_b200_build_info": (ctypes.c_char_p, []),
     "swiftly_b200_contribution_size": (ctypes.c_int64, [_PLAN]),
+    "swiftly_b200_release_scratch": (None, [_PLAN]),
     "swiftly_b200_prepare_facet": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_prepare_facet_windowed": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),
     "swiftly_b200_extract_from_facet": (ctypes.c_int, [_PLAN, _LINES_P, _LINES_P, ctypes.c_int64, ctypes.c_void_p]),

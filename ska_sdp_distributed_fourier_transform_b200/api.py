@@ -403,6 +403,8 @@ class SwiftlyForward:
             # facets are dead from here on: drop the references held by the task list
             self.facet_tasks = [(cfg, None) for cfg, _ in self.facet_tasks]
             self.BF_Fs_persist = out
+            if hasattr(self.core, "release_scratch"):
+                self.core.release_scratch()  # stage 1's 2 GiB scratch is not needed any more
         return self.BF_Fs_persist
 
     # -- stage 2: per subgrid column ------------------------------------------------------

@@ -637,6 +637,10 @@ class SwiftlyCoreB200:
         _lib.check(self._lib, rc)
         return out
 
+    def release_scratch(self):
+        """Give the plan's scratch buffers (2 GiB after stage 1 at N = 65536) back to the device."""
+        self._lib.swiftly_b200_release_scratch(self._plan)
+
     # ------------------------------------------------------------------ rank-to-rank ordering
     def peer_signal(self, flag_table, n_peers, my_rank, value, stream_of):
         """Store ``value`` into entry ``my_rank`` of every rank's flag array (peer_sync.cu).

@@ -163,6 +163,24 @@ extern "C" void swiftly_b200_destroy(swiftly_b200* h) {
     delete h;
 }
 
+// Free the per-stream scratch buffers of the plan (the two-pass prepare_facet keeps up to 2 GiB
+// at N = 65536).  The streaming drivers call this once stage 1 is over, so that the memory is
+// available again to the caller's allocator; the small scratch lines of the split kernels are
+// re-created on demand.  Synchronises the streams that own a buffer.
+extern "C" void swiftly_b200_release_scratch(swiftly_b200* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
+    for (auto& kv : h->scratch) {
+        if (kv.second.first) {
+            cudaStreamSynchronize(kv.first);
+            cudaFree(kv.second.first);
+            kv.second.first = nullptr;
+            kv.second.second = 0;
+        }
+    }
+}
+
 extern "C" int64_t swiftly_b200_contribution_size(const swiftly_b200* h) { return h ? h->m : -1; }
 
 // test hook (not in the public header): force the 2 x n/2 split path

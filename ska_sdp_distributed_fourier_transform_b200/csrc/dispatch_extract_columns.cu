@@ -126,9 +126,11 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
         if (h->sg_variant != 7 && h->force_split != 1) {
             switch (n) {
                 case 16384: {
-                    // sg_variant 15: the 4 x Q form with a CTA-wide combine (measured equal to
-                    // 2 x 2Q); default: two fully independent groups (DIF across, DIT within)
-                    int rc = h->sg_variant == 15
+                    // default: the 4 x Q form with a CTA-wide combine; sg_variant 15: two fully
+                    // independent groups (DIF across, DIT within) -- measured SLOWER, 1.64 vs 1.33 ms
+                    // per 8 facets: its 16-byte stores at 32-byte stride cost more than the
+                    // combine phase and half of the scratch traffic it saves
+                    int rc = h->sg_variant != 15
                         ? launch_extract_tma4<4096, ExtractColumnsTma4Kernel<4096>>(h, op, max_fs, s, 4)
                         : (max_fs <= n / 2
                            ? launch_extract_tma4<4096, ExtractColumnsTmaDifKernel<4096, false>>(h, op, max_fs, s, 2)
@@ -138,7 +140,7 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
                 }
 #if defined(SWIFTLY_EMU)
                 case 512: {
-                    int rc = h->force_split == 3
+                    int rc = h->force_split != 3
                         ? launch_extract_tma4<128, ExtractColumnsTma4Kernel<128>>(h, op, max_fs, s, 4)
                         : (max_fs <= n / 2
                            ? launch_extract_tma4<128, ExtractColumnsTmaDifKernel<128, false>>(h, op, max_fs, s, 2)

@@ -375,7 +375,9 @@ struct ExtractColumnsTma4Kernel {
 // half the scratch traffic (each group parks only its own E0): the groups meet only at the
 // staging buffer (mbarrier wait at the top of a line, the second group past its last
 // first-pass load refills it).  The price: every group stores 16-byte samples at a 32-byte
-// stride (the other group fills the gaps; the sectors merge in L2).
+// stride (the other group fills the gaps; the sectors merge in L2) -- and the price is too
+// high: measured 1.64 ms per 8 facets against 1.33 ms for the 4 x Q form.  Kept selectable
+// (sg_variant 15) as a measured negative result.
 // BOTH: facets longer than yN/2 exist, z[j] and z[j + 2Q] may both be non-zero (two reads per
 // sample; the common fs <= yN/2 case reads one).
 template <int Q, bool BOTH>

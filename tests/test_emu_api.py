@@ -56,9 +56,9 @@ def test_emu_forward_backward_vs_oracle_kernel_variants(sg_variant):
 @pytest.mark.parametrize("force_split", [1, 2, 3])
 def test_emu_forward_split_k2_kernels(force_split):
     """K2 through the split kernels that serve yN = 16384 on the GPU, forced at yN = 512:
-    1 = 2 x 256 (one thread group, E parked in the scratch), 2 = two independent thread groups
-    (DIF across the groups, DIT within) on the same TMA-staged, swizzled row, 3 = 4 x 128 with a
-    CTA-wide combine."""
+    1 = 2 x 256 (one thread group, E parked in the scratch), 2 = 4 x 128 with two thread groups
+    on the same TMA-staged, swizzled row and a CTA-wide combine (the default at yN = 16384),
+    3 = two fully independent groups (DIF across the groups, DIT within)."""
     import numpy
 
     from oracle.swiftly_oracle import OracleCore, forward_reference_order
