@@ -133,6 +133,7 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        power = []
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -152,6 +153,10 @@ class ClockSampler:
                     maxc.append(float(parts[2]))
                 except ValueError:
                     continue
+                try:
+                    power.append(float(parts[3]))
+                except ValueError:
+                    pass
                 for name, val in zip(names, parts[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
@@ -163,6 +168,11 @@ class ClockSampler:
             out["sm_mhz"] = float(numpy.median(clocks))
             out["sm_max_mhz"] = float(max(maxc))
             out["samples"] = len(clocks)
+            out["sm_mhz_min"] = float(min(clocks))
+            out["sm_mhz_p10"] = float(numpy.percentile(clocks, 10))
+            if power:
+                out["power_w_median"] = float(numpy.median(power))
+                out["power_w_max"] = float(max(power))
         out["reasons"] = sorted(reasons)
         return out
 

@@ -199,7 +199,6 @@ class SwiftlyForwardSharded:
                 self.launches += 1
                 del facet
             self._local_facets = {}
-            self.core.release_scratch()  # stage 1's scratch is not needed any more
         return self.BF_Fs
 
     def _column(self, off0):
