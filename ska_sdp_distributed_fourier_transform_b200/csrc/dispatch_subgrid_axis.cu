@@ -67,6 +67,10 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
     k.tma_per_group = a.out_g[0] != nullptr ? 1 : 0;
     k.pf_mode = h->sg_variant == 11 ? 1 : (h->sg_variant == 12 ? 2 : 0);
     k.stagger_ns = h->sg_variant == 13 ? 5000 : (h->sg_variant == 14 ? 2500 : 0);
+    // sg_variant 16: the first round exchanges complex samples through the (still empty)
+    // accumulator.  Measured SLOWER (0.604 vs 0.564 ms): the group barrier it needs before the
+    // round's stores re-aligns the transforms that the split-exchange form lets drift apart.
+    k.cx_round0 = (h->sg_variant == 16 && XM == (XM / M) * M && M > 16) ? 1 : 0;
     // (the last box may be partial: the engine still reads a whole box from shared memory)
     const size_t staged = (size_t)((a.sz + k.tma_box - 1) / (k.tma_box > 0 ? k.tma_box : 1)) *
                           (size_t)k.tma_box * sizeof(cplx);

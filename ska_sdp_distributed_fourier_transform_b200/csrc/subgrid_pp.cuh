@@ -75,6 +75,7 @@ struct SubgridAxisKernelPP {
     int tma_slot_line, tma_slot_elem, tma_slot_group;  // coordinate slots (1..3)
     int tma_per_group;                 // one tensor map per group (groups in different buffers)
     int stagger_ns;                    // group 1 starts this much later than group 0 (see below)
+    int cx_round0;                     // first round exchanges complex samples in the accumulator
     int pf_mode;                       // L2 prefetch: 0 bulk at the first exchange (default),
                                        // 1 none, 2 per-thread prefetch at the start of the round
     cplx* out_g[SW_MAX_GROUPS];        // optional per-group output base (null: out + g * out_gs)
@@ -165,8 +166,8 @@ struct SubgridAxisKernelPP {
             const int64_t line = (gl - (int64_t)sgrp * pairs) * GROUPS + grp;
             const bool line_ok = line < n_lines;
             // the previous line's bulk stores must have read the staging (= work) buffer before
-            // the first exchange of this line writes it (see GroupSync::acquire)
-            msync.tma_pending = tma_out != 0;
+            // the first exchange THROUGH THE WORK AREA writes it (see GroupSync::acquire)
+            bool tma_wait_due = tma_out != 0;
             if (!first_round_tiles) {
                 for (int i = t; i < XM; i += T_X) acc[i] = mk(0.0, 0.0);
                 gsync();
@@ -238,9 +239,25 @@ struct SubgridAxisKernelPP {
                         }
                     }
                 }
-                msync.order_stores = slot0 > 0;
-                line_fft<M, -1>(lt, work + (size_t)c * WSTRIDE, tw_m, ld, st, msync);
+                if (tma_wait_due && !(overwrite && cx_round0)) {
+                    msync.tma_pending = true;
+                    tma_wait_due = false;
+                }
+                if (overwrite && cx_round0) {
+                    // First round of a tiling layout: the accumulator holds nothing yet, so its
+                    // storage serves as COMPLEX exchange buffers of the round's transforms (one
+                    // trip, two barriers per pass instead of two trips and four; CONC * (M +
+                    // M / 16) samples = exactly the accumulator's padded size).  The stores into
+                    // the accumulator then have to wait until every transform of the round has
+                    // left its buffer: the pre-store group barrier.
+                    msync.order_stores = true;
+                    line_fft_cx<M, -1, false>(lt, acc + (size_t)c * (M + M / 16), tw_m, ld, st, msync);
+                } else {
+                    msync.order_stores = slot0 > 0;
+                    line_fft<M, -1>(lt, work + (size_t)c * WSTRIDE, tw_m, ld, st, msync);
+                }
             }
+            if (tma_wait_due && t == 0) ctx.bulk_wait_read();  // (no round used the work area)
             gsync();  // accumulator complete
             {
                 cplx* o = (out_g[sgrp] ? out_g[sgrp] : out + (int64_t)sgrp * out_gs) + line * out_ls;

@@ -46,10 +46,11 @@ def test_emu_many_sources():
     api_cases.case_many_sources(make_config)
 
 
-@pytest.mark.parametrize("sg_variant", [0, 1, 2, 5])
+@pytest.mark.parametrize("sg_variant", [0, 1, 2, 5, 16])
 def test_emu_forward_backward_vs_oracle_kernel_variants(sg_variant):
     """Every variant of the fused subgrid kernel (0: two thread groups + TMA tensor stores,
-    1: round-1 kernel, 2: two groups with the LSU token, 5: two groups, direct stores)."""
+    1: round-1 kernel, 2: two groups with the LSU token, 5: two groups, direct stores,
+    16: first round with complex exchanges through the accumulator)."""
     api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)
 
 

@@ -43,7 +43,7 @@ def test_fused_backward_ops_vs_oracle():
                                                 xM=2048)
 
 
-@pytest.mark.parametrize("sg_variant", [0, 1, 2, 5])
+@pytest.mark.parametrize("sg_variant", [0, 1, 2, 5, 16])
 def test_forward_backward_vs_oracle_kernel_variants(sg_variant):
     """Every variant of the fused subgrid kernel against the oracle (N=2048, xA/xM = 0.5)."""
     api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)

@@ -96,6 +96,7 @@ int main() {
     k.scale = 1.0 / XM;
     k.first_round_tiles = 1;
     k.stagger_ns = 0;
+    k.cx_round0 = 0;
     long long* log;
     int* counts;
     cudaMalloc(&log, sizeof(long long) * grid * MAXEV);

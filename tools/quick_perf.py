@@ -99,7 +99,7 @@ big = [[torch.randn(m, yN, dtype=torch.complex128, device=dev) for _ in range(nf
 groups = [[(big[g][i], i * yB) for i in range(nf)] for g in range(nf)]
 for variant, name in ((1, "round-1 kernel"), (11, "two groups, no L2 prefetch"),
                       (12, "two groups, per-thread prefetch"), (13, "two groups, group 1 starts 5 us late"),
-                      (14, "two groups, group 1 starts 2.5 us late"), (0, "two groups, bulk prefetch (default)")):
+                      (16, "two groups, complex exchange through the accumulator in round 1"), (0, "two groups, bulk prefetch (default)")):
     core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
     t, ta = timeit(lambda: core.sum_finish_axis_grouped(groups, strips_t, axis=1, subgrid_off=2048))
     by = 16 * nf * (nf * m * m + m * xA)
