@@ -138,6 +138,7 @@ extern "C" int swiftly_b200_create(double W, int64_t N, int64_t xM, int64_t yN, 
     h->d_Fn = nullptr;
     h->force_split = 0;
     h->sg_variant = 0;
+    h->max_blocks = 0;
     cudaError_t e = cudaMalloc((void**)&h->d_Fb, sizeof(double) * (size_t)(yN > 1 ? yN - 1 : 1));
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_Fn, sizeof(double) * (size_t)h->m);
     if (e == cudaSuccess)
@@ -189,6 +190,10 @@ extern "C" void swiftly_b200_debug_force_split(swiftly_b200* h, int on) {
 }
 
 // test hook (not in the public header): select the fused subgrid kernel variant
+extern "C" void swiftly_b200_debug_max_blocks(swiftly_b200* h, int blocks) {
+    if (h) h->max_blocks = blocks;
+}
+
 extern "C" void swiftly_b200_debug_sg_variant(swiftly_b200* h, int variant) {
     if (h) h->sg_variant = variant;
 }

@@ -83,6 +83,17 @@ SW_HD void st_stream(cplx* p, cplx v) {
 #endif
 }
 
+// two adjacent samples (32 bytes, 32-byte aligned) in ONE streaming store (STG.256 on sm_100)
+SW_HD void st_stream_pair(cplx* p, cplx a, cplx b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x),
+                 "d"(b.y) : "memory");
+#else
+    p[0] = a;
+    p[1] = b;
+#endif
+}
+
 // software prefetch of the 32-byte sector(s) holding *p into L2 (no register is tied up):
 // all warps of a CTA are in the same phase of a transform, so a plain load at the start of
 // the next phase exposes the full DRAM latency; the prefetch is issued one phase ahead
@@ -209,6 +220,59 @@ struct DeviceCtx {
     __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) const {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes)
                      : "memory");
+    }
+    // ---- tensor memory (TMEM: 128 lanes x 512 columns x 32 bit per SM) as PARKING SPACE ----
+    // No tensor-core instruction is involved: TMEM is used as a second register file.  A warp
+    // reaches the 32 lanes of its own quarter (warp id mod 4), every thread its own lane, any
+    // column: a sample a thread parks (tcgen05.st) can be taken back by the same thread, or --
+    // after fence / barrier / fence -- by the thread with the same lane number in a warp of the
+    // same quarter.  `lane` (0..127) must be 32 * (warp id mod 4) + lane id of the caller (the
+    // host emulation has no warps and takes it literally); `col` is a multiple of 4 (one
+    // complex128 sample = four 32-bit columns).
+    // All threads call; warp 0 allocates `cols` (a power of two >= 32) columns.  Contains a CTA
+    // barrier.  Every CTA that allocates MUST call tmem_free before it exits.
+    __device__ __forceinline__ uint32_t tmem_alloc(uint32_t* smem_slot, int cols) const {
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(smem_slot)), "r"(cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        return *(volatile uint32_t*)smem_slot;
+    }
+    __device__ __forceinline__ void tmem_free(uint32_t base, int cols) const {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols)
+                         : "memory");
+    }
+    __device__ __forceinline__ void tmem_st(uint32_t base, int lane, int col, cplx v) const {
+        const uint32_t taddr = base + (((uint32_t)lane & ~31u) << 16) + (uint32_t)col;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr),
+                     "r"(__double2loint(v.x)), "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)),
+                     "r"(__double2hiint(v.y)) : "memory");
+    }
+    // (the load is complete on return)
+    __device__ __forceinline__ cplx tmem_ld(uint32_t base, int lane, int col) const {
+        const uint32_t taddr = base + (((uint32_t)lane & ~31u) << 16) + (uint32_t)col;
+        int a, b, c, d;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+        // (the registers pass THROUGH the wait so that no use of them can be scheduled before it)
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)::"memory");
+        return mk(__hiloint2double(b, a), __hiloint2double(d, c));
+    }
+    __device__ __forceinline__ void tmem_wait_st() const {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    __device__ __forceinline__ void tmem_fence_before() const {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __device__ __forceinline__ void tmem_fence_after() const {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
 };
 

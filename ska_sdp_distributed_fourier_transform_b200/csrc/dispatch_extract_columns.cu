@@ -2,6 +2,7 @@
 // the heavy FP64 template instantiations compiling in parallel).
 #include "dispatch.cuh"
 #include "extract_tma.cuh"
+#include "extract_tmem.cuh"
 
 namespace swiftly {
 
@@ -49,6 +50,7 @@ static int launch_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op,
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)148 * per_sm;
     if (blocks > op.g.n_lines) blocks = op.g.n_lines;
+    if (h->max_blocks > 0 && blocks > h->max_blocks) blocks = h->max_blocks;
     k.scratch = nullptr;
     if (SPLIT) {
         k.scratch = split_scratch(h, s, (size_t)blocks * H);
@@ -99,11 +101,27 @@ static int launch_extract_tma4(const swiftly_b200* h, const ExtractColumnsOp& op
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)148 * per_sm;
     if (blocks > op.g.n_lines) blocks = op.g.n_lines;
-    k.scratch = split_scratch(h, s, (size_t)blocks * scratch_lines * Q);
-    if (!k.scratch) return SWIFTLY_B200_ECUDA;
+    if (h->max_blocks > 0 && blocks > h->max_blocks) blocks = h->max_blocks;
+    k.scratch = nullptr;
+    if (scratch_lines > 0) {
+        k.scratch = split_scratch(h, s, (size_t)blocks * scratch_lines * Q);
+        if (!k.scratch) return SWIFTLY_B200_ECUDA;
+    }
     cudaError_t e = launch_body_maps(k, maps, (int)blocks, smem, s);
     return e == cudaSuccess ? SWIFTLY_B200_OK
                             : cuda_fail(e, "extract_columns (TMA, 4-way split) kernel launch");
+}
+
+// the TMEM kernel stores pairs of samples with one 32-byte store: every output line must start
+// on a 32-byte boundary
+static bool pair_store_ok(const ExtractColumnsOp& op, int n_facets) {
+    for (int f = 0; f < n_facets; ++f) {
+        if ((op.fac[f].out_ls & 1) != 0) return false;
+#if !defined(SWIFTLY_EMU)  // (the emulated pair store is two plain stores: host buffers are only 16-byte aligned)
+        if (((uintptr_t)op.fac[f].out & 31) != 0) return false;
+#endif
+    }
+    return true;
 }
 
 // returns -1 when the TMA-staged kernel does not apply (then the generic kernels run)
@@ -126,6 +144,24 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
         if (h->sg_variant != 7 && h->force_split != 1) {
             switch (n) {
                 case 16384: {
+                    // sg_variant 17: intermediate results parked in tensor memory, the two
+                    // groups swap halves through it and store 32-byte pairs (extract_tmem.cuh)
+                    // sg_variant 18: the same with decimation in time across the groups
+                    if (h->sg_variant == 17 && pair_store_ok(op, n_facets)) {
+                        int rc = max_fs <= n / 2
+                            ? launch_extract_tma4<4096, ExtractColumnsTmemKernel<4096, 0>>(h, op, max_fs, s, 0)
+                            : launch_extract_tma4<4096, ExtractColumnsTmemKernel<4096, 1>>(h, op, max_fs, s, 0);
+                        if (rc != -1) return rc;
+                    }
+                    if (h->sg_variant == 18) {
+                        int rc = launch_extract_tma4<4096, ExtractColumnsTmemKernel<4096, 2>>(h, op, max_fs, s, 0);
+                        if (rc != -1) return rc;
+                    }
+                    // sg_variant 19: ... and the store phases of the two groups half a line apart
+                    if (h->sg_variant == 19) {
+                        int rc = launch_extract_tma4<4096, ExtractColumnsTmemSkewKernel<4096>>(h, op, max_fs, s, 0);
+                        if (rc != -1) return rc;
+                    }
                     // default: the 4 x Q form with a CTA-wide combine; sg_variant 15: two fully
                     // independent groups (DIF across, DIT within) -- measured SLOWER, 1.64 vs 1.33 ms
                     // per 8 facets: its 16-byte stores at 32-byte stride cost more than the
@@ -140,6 +176,20 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
                 }
 #if defined(SWIFTLY_EMU)
                 case 512: {
+                    if (h->force_split == 4 && pair_store_ok(op, n_facets)) {
+                        int rc = max_fs <= n / 2
+                            ? launch_extract_tma4<128, ExtractColumnsTmemKernel<128, 0>>(h, op, max_fs, s, 0)
+                            : launch_extract_tma4<128, ExtractColumnsTmemKernel<128, 1>>(h, op, max_fs, s, 0);
+                        if (rc != -1) return rc;
+                    }
+                    if (h->force_split == 5) {
+                        int rc = launch_extract_tma4<128, ExtractColumnsTmemKernel<128, 2>>(h, op, max_fs, s, 0);
+                        if (rc != -1) return rc;
+                    }
+                    if (h->force_split == 6) {
+                        int rc = launch_extract_tma4<128, ExtractColumnsTmemSkewKernel<128>>(h, op, max_fs, s, 0);
+                        if (rc != -1) return rc;
+                    }
                     int rc = h->force_split != 3
                         ? launch_extract_tma4<128, ExtractColumnsTma4Kernel<128>>(h, op, max_fs, s, 4)
                         : (max_fs <= n / 2

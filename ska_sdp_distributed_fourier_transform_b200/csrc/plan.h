@@ -22,6 +22,8 @@ struct swiftly_b200 {
     mutable std::map<cudaStream_t, std::pair<swiftly::cplx*, size_t>> scratch;
     int force_split;  // debug / test: transform yN lines with the 2 x yN/2 split path
     int sg_variant;   // debug / test: fused subgrid kernel variant (dispatch_subgrid_axis.cu)
+    int max_blocks;   // debug / test: cap of the persistent kernels' grid (0: none), so that a
+                      // small test problem walks several lines per CTA
 };
 
 namespace swiftly {

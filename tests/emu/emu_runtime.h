@@ -105,6 +105,16 @@ struct HostCtx {
     inline void bulk_wait_all() const {}
     inline void tensor_store(const void* map, const void* smem_src, int c1, int c2, int c3) const;
     inline void tensor_load(void* smem_dst, const void* map, int c1, int c2, uint64_t* bar) const;
+    // tensor memory as parking space: 128 lanes x 512 columns x 32 bit per CTA; the emulation
+    // takes (lane, column) literally (no warps: the kernel's own lane arithmetic is what is
+    // tested), poisons the allocation and rejects accesses outside of it
+    inline uint32_t tmem_alloc(uint32_t* smem_slot, int cols) const;
+    inline void tmem_free(uint32_t base, int cols) const;
+    inline void tmem_st(uint32_t base, int lane, int col, double2 v) const;
+    inline double2 tmem_ld(uint32_t base, int lane, int col) const;
+    inline void tmem_wait_st() const {}
+    inline void tmem_fence_before() const {}
+    inline void tmem_fence_after() const {}
 };
 
 }  // namespace swiftly
@@ -135,6 +145,8 @@ struct EmuBlock {
     int bar_arrived[16];
     unsigned bar_gen[16];
     unsigned long progress;  // barrier completions + thread exits (deadlock detection)
+    std::vector<uint32_t> tmem;  // 128 lanes x 512 columns
+    int tmem_cols;               // allocated columns (0: none)
 };
 
 static EmuBlock* g_emu_block = nullptr;
@@ -161,6 +173,47 @@ inline void HostCtx::group_sync(int id, int count) const {
 }
 
 inline void HostCtx::sync() const { group_sync(0, blk->nthreads); }
+
+inline uint32_t HostCtx::tmem_alloc(uint32_t* smem_slot, int cols) const {
+    if (tid == 0) {
+        if (cols < 32 || cols > 512 || (cols & (cols - 1)) || blk->tmem_cols) {
+            fprintf(stderr, "swiftly emulator: bad TMEM allocation (%d columns)\n", cols);
+            abort();
+        }
+        blk->tmem.assign((size_t)128 * 512, 0xA5A5A5A5u);
+        blk->tmem_cols = cols;
+        *smem_slot = 0;
+    }
+    sync();
+    return *smem_slot;
+}
+inline void HostCtx::tmem_free(uint32_t, int cols) const {
+    sync();
+    if (tid == 0) {
+        if (cols != blk->tmem_cols) {
+            fprintf(stderr, "swiftly emulator: TMEM free of %d columns, %d allocated\n", cols,
+                    blk->tmem_cols);
+            abort();
+        }
+        blk->tmem_cols = 0;
+    }
+}
+static inline uint32_t* emu_tmem_cell(EmuBlock* b, uint32_t base, int lane, int col) {
+    if (lane < 0 || lane >= 128 || col < 0 || (col & 3) || (int)base + col + 4 > b->tmem_cols) {
+        fprintf(stderr, "swiftly emulator: TMEM access out of range (lane %d, column %d of %d)\n",
+                lane, (int)base + col, b->tmem_cols);
+        abort();
+    }
+    return &b->tmem[(size_t)lane * 512 + base + col];
+}
+inline void HostCtx::tmem_st(uint32_t base, int lane, int col, double2 v) const {
+    memcpy(emu_tmem_cell(blk, base, lane, col), &v, sizeof v);
+}
+inline double2 HostCtx::tmem_ld(uint32_t base, int lane, int col) const {
+    double2 v;
+    memcpy(&v, emu_tmem_cell(blk, base, lane, col), sizeof v);
+    return v;
+}
 
 static void emu_trampoline() {
     EmuBlock* b = g_emu_block;
@@ -226,6 +279,7 @@ inline cudaError_t launch_body_impl(const Body& body, const void* tmaps, int gri
             blk.bar_gen[i] = 0;
         }
         blk.progress = 0;
+        blk.tmem_cols = 0;
         bool any = true;
         int idle_sweeps = 0;
         while (any) {
@@ -246,6 +300,10 @@ inline cudaError_t launch_body_impl(const Body& body, const void* tmaps, int gri
                 fprintf(stderr, ")\n");
                 abort();
             }
+        }
+        if (blk.tmem_cols) {
+            fprintf(stderr, "swiftly emulator: block %d exits with TMEM still allocated\n", bid);
+            abort();
         }
     }
     free(smem);

@@ -54,12 +54,17 @@ def test_emu_forward_backward_vs_oracle_kernel_variants(sg_variant):
     api_cases.case_forward_backward_vs_oracle(make_config, sg_variant=sg_variant)
 
 
-@pytest.mark.parametrize("force_split", [1, 2, 3])
+@pytest.mark.parametrize("force_split", [1, 2, 3, 4, 5, 6])
 def test_emu_forward_split_k2_kernels(force_split):
     """K2 through the split kernels that serve yN = 16384 on the GPU, forced at yN = 512:
     1 = 2 x 256 (one thread group, E parked in the scratch), 2 = 4 x 128 with two thread groups
     on the same TMA-staged, swizzled row and a CTA-wide combine (the default at yN = 16384),
-    3 = two fully independent groups (DIF across the groups, DIT within)."""
+    3 = two fully independent groups (DIF across the groups, DIT within), 4 = the same
+    decomposition with the intermediate results parked in (emulated) tensor memory and the
+    groups swapping halves through it before 32-byte pair stores, 5 = tensor-memory parking
+    with decimation in time across the groups as well (unit-stride output streams), 6 = the
+    same with group 1's stores of a line deferred into the next line (kept half in tensor
+    memory, bar.arrive / bar.sync hand-over of the parked half)."""
     import numpy
 
     from oracle.swiftly_oracle import OracleCore, forward_reference_order
@@ -82,6 +87,16 @@ def test_emu_forward_split_k2_kernels(force_split):
     for a, b, c in zip(got, ref, ref2):
         assert numpy.abs(a - (b + c)).max() <= 1e-12 * numpy.abs(b + c).max()
     # only the facets whose rows are whole 128-byte chunks: staged by swizzled tensor loads
+    fwd = SwiftlyForward(cfg, [(FacetConfig(a, b, yB), f) for (a, b), f in zip(offs[:2], facets)])
+    for sg, b in zip(sgs, ref):
+        a = fwd.get_subgrid_task(sg).result()
+        assert numpy.abs(a - b).max() <= 1e-12 * numpy.abs(b).max()
+    # persistent CTAs that walk SEVERAL lines each (grid capped at 5 CTAs: 51-52 lines per CTA
+    # -- staging refills, tensor-memory double buffering, stores deferred into the next line)
+    import ctypes
+
+    cfg.core._lib.swiftly_b200_debug_max_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    cfg.core._lib.swiftly_b200_debug_max_blocks(cfg.core._plan, 5)
     fwd = SwiftlyForward(cfg, [(FacetConfig(a, b, yB), f) for (a, b), f in zip(offs[:2], facets)])
     for sg, b in zip(sgs, ref):
         a = fwd.get_subgrid_task(sg).result()
