@@ -265,6 +265,28 @@ struct DeviceCtx {
         asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)::"memory");
         return mk(__hiloint2double(b, a), __hiloint2double(d, c));
     }
+    // split form: several loads in flight, one wait.  The destination registers must not be
+    // touched between issue and wait: they pass through the wait statement as in/out operands.
+    struct TmemLoad {
+        int r[4];
+    };
+    __device__ __forceinline__ void tmem_ld_issue(uint32_t base, int lane, int col, TmemLoad& t) const {
+        const uint32_t taddr = base + (((uint32_t)lane & ~31u) << 16) + (uint32_t)col;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(t.r[0]), "=r"(t.r[1]), "=r"(t.r[2]), "=r"(t.r[3]) : "r"(taddr) : "memory");
+    }
+    __device__ __forceinline__ cplx tmem_ld_wait(TmemLoad& t) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(t.r[0]), "+r"(t.r[1]), "+r"(t.r[2]), "+r"(t.r[3])::"memory");
+        return mk(__hiloint2double(t.r[1], t.r[0]), __hiloint2double(t.r[3], t.r[2]));
+    }
+    __device__ __forceinline__ void tmem_ld_wait2(TmemLoad& t, TmemLoad& u, cplx& a, cplx& b) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(t.r[0]), "+r"(t.r[1]), "+r"(t.r[2]), "+r"(t.r[3]), "+r"(u.r[0]),
+                       "+r"(u.r[1]), "+r"(u.r[2]), "+r"(u.r[3])::"memory");
+        a = mk(__hiloint2double(t.r[1], t.r[0]), __hiloint2double(t.r[3], t.r[2]));
+        b = mk(__hiloint2double(u.r[1], u.r[0]), __hiloint2double(u.r[3], u.r[2]));
+    }
     __device__ __forceinline__ void tmem_wait_st() const {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }

@@ -144,9 +144,13 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
         if (h->sg_variant != 7 && h->force_split != 1) {
             switch (n) {
                 case 16384: {
-                    // sg_variant 17: intermediate results parked in tensor memory, the two
-                    // groups swap halves through it and store 32-byte pairs (extract_tmem.cuh)
-                    // sg_variant 18: the same with decimation in time across the groups
+                    // DEFAULT (extract_tmem.cuh): intermediate results parked in tensor memory,
+                    // decimation in time within and across the two thread groups, the groups swap
+                    // halves through TMEM, their store phases half a line apart.  Measured per 8
+                    // facets of pre-windowed rows: 0.87 ms (0.56 of the HBM roofline) against 1.18
+                    // for the 4 x Q form with the L2 scratch below (now sg_variant 20).
+                    // sg_variant 18: the same without the skew of the store phases (0.99 ms);
+                    // sg_variant 17: DIF across the groups, 32-byte pair stores (1.13 ms)
                     if (h->sg_variant == 17 && pair_store_ok(op, n_facets)) {
                         int rc = max_fs <= n / 2
                             ? launch_extract_tma4<4096, ExtractColumnsTmemKernel<4096, 0>>(h, op, max_fs, s, 0)
@@ -157,12 +161,11 @@ static int try_extract_tma(const swiftly_b200* h, const ExtractColumnsOp& op, cu
                         int rc = launch_extract_tma4<4096, ExtractColumnsTmemKernel<4096, 2>>(h, op, max_fs, s, 0);
                         if (rc != -1) return rc;
                     }
-                    // sg_variant 19: ... and the store phases of the two groups half a line apart
-                    if (h->sg_variant == 19) {
+                    if (h->sg_variant != 20 && h->sg_variant != 15) {
                         int rc = launch_extract_tma4<4096, ExtractColumnsTmemSkewKernel<4096>>(h, op, max_fs, s, 0);
                         if (rc != -1) return rc;
                     }
-                    // default: the 4 x Q form with a CTA-wide combine; sg_variant 15: two fully
+                    // sg_variant 20: the 4 x Q form with a CTA-wide combine; sg_variant 15: two fully
                     // independent groups (DIF across, DIT within) -- measured SLOWER, 1.64 vs 1.33 ms
                     // per 8 facets: its 16-byte stores at 32-byte stride cost more than the
                     // combine phase and half of the scratch traffic it saves

@@ -397,6 +397,10 @@ struct ExtractColumnsTmemSkewKernel : ExtractColumnsTmemKernel<Q, 2> {
         auto store_prev = [&](int a_col, int b_col) {
             const cplx w_r = this->root(LP::NS % N);
             cplx w = mk(1.0, 0.0);
+            // the TMEM loads of slot s + 1 are in flight while slot s is combined and stored
+            typename Ctx::TmemLoad la, lb;
+            if (grp) ctx.tmem_ld_issue(tbase, tl, a_col, la);
+            ctx.tmem_ld_issue(tbase, tl, b_col, lb);
 #pragma unroll
             for (int it = 0; it < LP::ITERS; ++it) {
                 const int j = tg + it * TG;
@@ -406,8 +410,18 @@ struct ExtractColumnsTmemSkewKernel : ExtractColumnsTmemKernel<Q, 2> {
                     const int s = it * LP::R + r;
                     const int kk = base + r * LP::NS + (grp ? Q : 0);
                     w = r == 0 ? this->root(kk % N) : cmul(w, w_r);
-                    const cplx a = grp ? ctx.tmem_ld(tbase, tl, a_col + 4 * s) : keep[s];
-                    const cplx wb = cmul(ctx.tmem_ld(tbase, tl, b_col + 4 * s), w);
+                    cplx a, b;
+                    if (grp) {
+                        ctx.tmem_ld_wait2(la, lb, a, b);
+                    } else {
+                        a = keep[s];
+                        b = ctx.tmem_ld_wait(lb);
+                    }
+                    if (s + 1 < 16) {
+                        if (grp) ctx.tmem_ld_issue(tbase, tl, a_col + 4 * (s + 1), la);
+                        ctx.tmem_ld_issue(tbase, tl, b_col + 4 * (s + 1), lb);
+                    }
+                    const cplx wb = cmul(b, w);
                     st_stream(o_prev + wrap_add(kk, n / 2, n), cadd(a, wb));
                     st_stream(o_prev + wrap_add(kk + H, n / 2, n), csub(a, wb));
                 }
@@ -458,6 +472,7 @@ struct ExtractColumnsTmemSkewKernel : ExtractColumnsTmemKernel<Q, 2> {
                 auto ld = [&](int j) { return sample(4 * j + 2 + grp); };
                 const cplx v_it = this->root((2 * TG) % N), v_r = this->root((2 * LP::NS) % N);
                 cplx w_it = mk(1.0, 0.0), w = mk(1.0, 0.0);
+                typename Ctx::TmemLoad le;
                 auto st = [&](int k, cplx od, int it, int r) {
                     if (r == 0) {
                         w_it = it == 0 ? this->root((2 * k) % N) : cmul(w_it, v_it);
@@ -466,7 +481,10 @@ struct ExtractColumnsTmemSkewKernel : ExtractColumnsTmemKernel<Q, 2> {
                         w = cmul(w, v_r);
                     }
                     const int s = it * LP::R + r;
-                    const cplx e = ctx.tmem_ld(tbase, tl, col0 + 4 * s);
+                    // (E0 of slot s + 1 is in flight while slot s is combined and parked)
+                    if (s == 0) ctx.tmem_ld_issue(tbase, tl, col0, le);
+                    const cplx e = ctx.tmem_ld_wait(le);
+                    if (s + 1 < 16) ctx.tmem_ld_issue(tbase, tl, col0 + 4 * (s + 1), le);
                     const cplx wo = cmul(od, w);
                     const cplx lo = cscale(cadd(e, wo), scale);
                     const cplx hi = cscale(csub(e, wo), scale);

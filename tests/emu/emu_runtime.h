@@ -112,6 +112,17 @@ struct HostCtx {
     inline void tmem_free(uint32_t base, int cols) const;
     inline void tmem_st(uint32_t base, int lane, int col, double2 v) const;
     inline double2 tmem_ld(uint32_t base, int lane, int col) const;
+    struct TmemLoad {
+        double2 v;
+    };
+    inline void tmem_ld_issue(uint32_t base, int lane, int col, TmemLoad& t) const {
+        t.v = tmem_ld(base, lane, col);
+    }
+    inline double2 tmem_ld_wait(TmemLoad& t) const { return t.v; }
+    inline void tmem_ld_wait2(TmemLoad& t, TmemLoad& u, double2& a, double2& b) const {
+        a = t.v;
+        b = u.v;
+    }
     inline void tmem_wait_st() const {}
     inline void tmem_fence_before() const {}
     inline void tmem_fence_after() const {}

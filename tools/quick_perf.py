@@ -56,7 +56,8 @@ by = 16 * (m * yB + m * yN) * nf
 keep = None
 for variant, name in ((4, "round-1 kernel"), (7, "TMA rows, 2 x (yN/2), swizzled"),
                       (15, "TMA rows, two independent groups (DIF across / DIT within)"),
-                      (0, "TMA rows, default (4 x 4096, two groups + CTA-wide combine)")):
+                      (20, "TMA rows, 4 x 4096, two groups + CTA-wide combine, L2 scratch"),
+                      (0, "TMA rows, default (DIT / DIT, TMEM parking + swap, skewed stores)")):
     core._lib.swiftly_b200_debug_sg_variant(core._plan, variant)
     t, ta = timeit(lambda: core.extract_columns(bfs, 4096, offs, outs=nmbf))
     print(f"F2 extract_columns x{nf} [{name}]: {t:.3f} ms (avg {ta:.3f})  frac {by/t*1e3/HBM:.3f}")
