@@ -67,6 +67,11 @@ static int launch_sg_axis_pp(const swiftly_b200* h, const SubgridAxisArgs& a, cu
     k.tma_per_group = a.out_g[0] != nullptr ? 1 : 0;
     k.pf_mode = h->sg_variant == 11 ? 1 : (h->sg_variant == 12 ? 2 : 0);
     k.stagger_ns = h->sg_variant == 13 ? 5000 : (h->sg_variant == 14 ? 2500 : 0);
+    // CTA b starts (b mod 16) * 400 ns late: all CTAs of a launch run identical work and would
+    // stay in phase chip-wide (every SM loading at the same moment, then none).  Measured (cfg4,
+    // one subgrid): axis 1 0.566 -> 0.554 ms, axis 0 0.158 -> 0.153 ms, both back to back 0.734 ->
+    // 0.709 ms; 800 ns the same, 1300 ns slower.  sg_variant 24: no stagger; 22 / 23: 800 / 1300 ns
+    k.stagger_cta_ns = h->sg_variant == 24 ? 0 : (h->sg_variant == 22 ? 800 : (h->sg_variant == 23 ? 1300 : 400));
     // sg_variant 16: the first round exchanges complex samples through the (still empty)
     // accumulator.  Measured SLOWER (0.604 vs 0.564 ms): the group barrier it needs before the
     // round's stores re-aligns the transforms that the split-exchange form lets drift apart.

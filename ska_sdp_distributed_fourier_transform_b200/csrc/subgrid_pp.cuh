@@ -75,6 +75,7 @@ struct SubgridAxisKernelPP {
     int tma_slot_line, tma_slot_elem, tma_slot_group;  // coordinate slots (1..3)
     int tma_per_group;                 // one tensor map per group (groups in different buffers)
     int stagger_ns;                    // group 1 starts this much later than group 0 (see below)
+    int stagger_cta_ns;                // CTA b starts (b mod 16) * this much later (see below)
     int cx_round0;                     // first round exchanges complex samples in the accumulator
     int pf_mode;                       // L2 prefetch: 0 bulk at the first exchange (default),
                                        // 1 none, 2 per-thread prefetch at the start of the round
@@ -158,6 +159,13 @@ struct SubgridAxisKernelPP {
         // other group's m-point rounds.
         if (grp == 1 && stagger_ns > 0) {
             for (int left = stagger_ns; left > 0; left -= 1000) ctx.nap(1000);
+        }
+        // All CTAs of a launch start together and run identical work: chip-wide, the load phases
+        // of every SM fall onto each other (HBM sees bursts) and so do the phases that leave the
+        // memory system idle.  Spreading the start times over about one line de-phases the SMs.
+        if (stagger_cta_ns > 0) {
+            for (int left = (int)(ctx.bid % 16) * stagger_cta_ns; left > 0; left -= 1000)
+                ctx.nap(left < 1000 ? left : 1000);
         }
         const int64_t pairs = (n_lines + GROUPS - 1) / GROUPS;  // line pairs per source group
         const int64_t total = pairs * n_groups;
