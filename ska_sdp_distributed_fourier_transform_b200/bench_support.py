@@ -269,6 +269,20 @@ class ForwardBenchRunner:
         srcs0 = [(strips[r], row_offs[r]) for r in range(nstrips)]
         t4 = self._time(lambda: core.sum_finish_axis(srcs0, res, axis=0, subgrid_off=sg.off0))
         out["sum_finish_axis0 (per subgrid)"] = (t4, 16.0 * (nstrips * m * xA + xA * xA), owned_sg)
+        # FP64 rate next to every HBM fraction: nominal flops (5 n log2 n per n-point transform)
+        # per launch, keyed by the first word of the kernel name
+        def fft_flops(n):
+            return 5.0 * n * float(numpy.log2(n))
+
+        xM = self.xM
+        nominal = {
+            "prepare_facet_axis0": yB * fft_flops(yN),
+            "extract_columns": F * m * fft_flops(yN),
+            "sum_finish_axis1": F * m * fft_flops(m) + len(groups) * m * fft_flops(xM),
+            "sum_finish_axis0": xA * (nstrips * fft_flops(m) + fft_flops(xM)),
+        }
+        if self.world > 1:
+            nominal["sum_finish_axis1"] *= len(batch)
         kernels = []
         total = sum(t * n for t, _, n in out.values())
         for name, (t, by, n) in out.items():
@@ -277,6 +291,7 @@ class ForwardBenchRunner:
                 "kernel": name, "avg_ms": t, "launches_per_step": n,
                 "algorithmic_bytes_per_launch": by, "achieved": ach, "unit": "GB/s",
                 "frac": ach / hbm_gbs, "share_of_kernel_time": t * n / total,
+                "fp64_nominal_tflops": nominal.get(name.split(" ")[0], 0.0) / (t * 1e-3) / 1e12,
             })
         dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
         dominant = {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_gbs, "unit": "GB/s",

@@ -101,3 +101,33 @@ def test_emu_forward_split_k2_kernels(force_split):
     for sg, b in zip(sgs, ref):
         a = fwd.get_subgrid_task(sg).result()
         assert numpy.abs(a - b).max() <= 1e-12 * numpy.abs(b).max()
+
+
+@pytest.mark.parametrize("force_split", [1, 2, 3, 4, 5, 6])
+def test_emu_k2_forms_long_and_odd_rows(force_split):
+    """``extract_columns`` of every K2 form (see test_emu_forward_split_k2_kernels) against the
+    oracle on rows LONGER than yN / 2 (both halves of the DIF forms' first step are non-zero) and
+    of odd length (linear bulk copies instead of swizzled tensor loads), a few lines per CTA."""
+    import ctypes
+
+    import numpy
+    import torch
+
+    from oracle.swiftly_oracle import OracleCore
+    from tests import parity_cases as pc
+
+    W, N, yB, yN, xA, xM = 13.5625, 1024, 256, 512, 128, 256
+    cfg = make_config(W, N, yB, yN, xA, xM, force_split=force_split)
+    core = cfg.core
+    core._lib.swiftly_b200_debug_max_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    core._lib.swiftly_b200_debug_max_blocks(core._plan, 7)
+    oracle = OracleCore(W, N, xM, yN)
+    rng = numpy.random.default_rng(40 + force_split)
+    sg_off0 = 3 * xA
+    for sizes, offs in (((320, 320), (0, 256)), ((301, 257), (-256, 512))):
+        bfs = [pc.rand_c(rng, yN, fs) for fs in sizes]
+        refs = [oracle.prepare_facet(oracle.extract_from_facet(bf, sg_off0, axis=0), off1, axis=1)
+                for bf, off1 in zip(bfs, offs)]
+        outs = core.extract_columns([torch.from_numpy(bf.copy()) for bf in bfs], sg_off0, list(offs))
+        for o, r in zip(outs, refs):
+            assert numpy.abs(o.numpy() - r).max() <= 1e-12 * numpy.abs(r).max()
