@@ -22,6 +22,34 @@
 
 namespace swiftly {
 
+// Start the asynchronous copy of the input row of output line `line` into the staging buffer
+// `in` (called by ONE thread; completion on the mbarrier `bar`): bulk TENSOR loads with the
+// 128-byte swizzle when the rows are whole 128-byte chunks (tensor_map.cu make_row_map; a box
+// that sticks out of the row is zero filled and still counts in full), else 1-D bulk copies in
+// pieces of at most 64 KiB.  Shared by all TMA-staged K2 kernels.
+template <class Maps, class Ctx>
+SW_HD void k2_issue_row(const Ctx& ctx, const ExtractColumnsOp& op, int swizzled, int box_chunks,
+                        cplx* in, uint64_t* bar, int64_t line) {
+    const int f = (int)(line / op.lines_per);
+    const int l = (int)(line - (int64_t)f * op.lines_per);
+    const ColumnFacet& F = op.fac[f];
+    const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
+    if (swizzled) {
+        const int chunks = F.fs / 8;
+        const int boxes = (chunks + box_chunks - 1) / box_chunks;
+        ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
+        for (int c0 = 0; c0 < chunks; c0 += box_chunks)
+            ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
+                            (int)row, bar);
+        return;
+    }
+    const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
+    ctx.tx_expect(bar, bytes);
+    const char* src = (const char*)(F.in + row * F.in_ls);
+    for (uint32_t o = 0; o < bytes; o += 65536u)
+        ctx.tx_copy((char*)in + o, src + o, bytes - o < 65536u ? bytes - o : 65536u, bar);
+}
+
 template <int H, bool SPLIT>
 struct ExtractColumnsTmaKernel {
     static constexpr int DIR = +1;
@@ -69,29 +97,7 @@ struct ExtractColumnsTmaKernel {
 
     template <class Ctx>
     SW_HD void issue(const Ctx& ctx, cplx* in, uint64_t* bar, int64_t line) const {
-        const int f = (int)(line / op.lines_per);
-        const int l = (int)(line - (int64_t)f * op.lines_per);
-        const ColumnFacet& F = op.fac[f];
-        const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
-        if (swizzled) {
-            const int chunks = F.fs / 8;
-            const int boxes = (chunks + box_chunks - 1) / box_chunks;
-            // (a box that sticks out of the row is zero filled and still counts in full)
-            ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
-            for (int c0 = 0; c0 < chunks; c0 += box_chunks)
-                ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
-                                (int)row, bar);
-            return;
-        }
-        const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
-        ctx.tx_expect(bar, bytes);
-        // one bulk copy may not exceed the engine's size field comfortably: 64 KiB pieces
-        const char* src = (const char*)(F.in + row * F.in_ls);
-        char* dst = (char*)in;
-        for (uint32_t o = 0; o < bytes; o += 65536u) {
-            const uint32_t n = bytes - o < 65536u ? bytes - o : 65536u;
-            ctx.tx_copy(dst + o, src + o, n, bar);
-        }
+        k2_issue_row<Maps>(ctx, op, swizzled, box_chunks, in, bar, line);
     }
 
     template <class Ctx>
@@ -224,24 +230,7 @@ struct ExtractColumnsTma4Kernel {
 
     template <class Ctx>
     SW_HD void issue(const Ctx& ctx, cplx* in, uint64_t* bar, int64_t line) const {
-        const int f = (int)(line / op.lines_per);
-        const int l = (int)(line - (int64_t)f * op.lines_per);
-        const ColumnFacet& F = op.fac[f];
-        const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
-        if (swizzled) {
-            const int chunks = F.fs / 8;
-            const int boxes = (chunks + box_chunks - 1) / box_chunks;
-            ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
-            for (int c0 = 0; c0 < chunks; c0 += box_chunks)
-                ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
-                                (int)row, bar);
-            return;
-        }
-        const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
-        ctx.tx_expect(bar, bytes);
-        const char* src = (const char*)(F.in + row * F.in_ls);
-        for (uint32_t o = 0; o < bytes; o += 65536u)
-            ctx.tx_copy((char*)in + o, src + o, bytes - o < 65536u ? bytes - o : 65536u, bar);
+        k2_issue_row<Maps>(ctx, op, swizzled, box_chunks, in, bar, line);
     }
 
     // group barrier; after the first-pass loads of the group's LAST sub-transform the staging
@@ -412,24 +401,7 @@ struct ExtractColumnsTmaDifKernel {
 
     template <class Ctx>
     SW_HD void issue(const Ctx& ctx, cplx* in, uint64_t* bar, int64_t line) const {
-        const int f = (int)(line / op.lines_per);
-        const int l = (int)(line - (int64_t)f * op.lines_per);
-        const ColumnFacet& F = op.fac[f];
-        const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
-        if (swizzled) {
-            const int chunks = F.fs / 8;
-            const int boxes = (chunks + box_chunks - 1) / box_chunks;
-            ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
-            for (int c0 = 0; c0 < chunks; c0 += box_chunks)
-                ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
-                                (int)row, bar);
-            return;
-        }
-        const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
-        ctx.tx_expect(bar, bytes);
-        const char* src = (const char*)(F.in + row * F.in_ls);
-        for (uint32_t o = 0; o < bytes; o += 65536u)
-            ctx.tx_copy((char*)in + o, src + o, bytes - o < 65536u ? bytes - o : 65536u, bar);
+        k2_issue_row<Maps>(ctx, op, swizzled, box_chunks, in, bar, line);
     }
 
     template <class Ctx>

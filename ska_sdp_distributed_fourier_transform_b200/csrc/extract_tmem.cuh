@@ -30,6 +30,7 @@
 // only (SASS: UTCATOMSWS, STTM, LDTM).
 #pragma once
 
+#include "extract_tma.cuh"
 #include "kernels.cuh"
 
 namespace swiftly {
@@ -86,24 +87,7 @@ struct ExtractColumnsTmemKernel {
 
     template <class Ctx>
     SW_HD void issue(const Ctx& ctx, cplx* in, uint64_t* bar, int64_t line) const {
-        const int f = (int)(line / op.lines_per);
-        const int l = (int)(line - (int64_t)f * op.lines_per);
-        const ColumnFacet& F = op.fac[f];
-        const int64_t row = wrap_add(op.rm_base, wrap_sub(l, op.rm_s_m, op.lines_per), op.n);
-        if (swizzled) {
-            const int chunks = F.fs / 8;
-            const int boxes = (chunks + box_chunks - 1) / box_chunks;
-            ctx.tx_expect(bar, (uint32_t)boxes * (uint32_t)box_chunks * 128u);
-            for (int c0 = 0; c0 < chunks; c0 += box_chunks)
-                ctx.tensor_load((char*)in + (size_t)c0 * 128, &((const Maps*)ctx.tmaps)->in_map[f], c0,
-                                (int)row, bar);
-            return;
-        }
-        const uint32_t bytes = (uint32_t)F.fs * (uint32_t)sizeof(cplx);
-        ctx.tx_expect(bar, bytes);
-        const char* src = (const char*)(F.in + row * F.in_ls);
-        for (uint32_t o = 0; o < bytes; o += 65536u)
-            ctx.tx_copy((char*)in + o, src + o, bytes - o < 65536u ? bytes - o : 65536u, bar);
+        k2_issue_row<Maps>(ctx, op, swizzled, box_chunks, in, bar, line);
     }
 
     // group barrier; after the first-pass loads of the group's LAST sub-transform the staging
