@@ -101,3 +101,42 @@ def test_core_pickles_by_parameters():
     state = core.__getstate__()
     assert state == {"W": 11.0, "N": 256, "xM_size": 64, "yN_size": 128, "device": 0}
     assert repr(core).endswith("(W=11.0, N=256, xM_size=64, yN_size=128)")
+
+
+_k2_cores = {}
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(form=st.sampled_from([2, 3, 4, 5, 6]), n_facets=st.integers(1, 3),
+       sizes=st.lists(st.integers(8, 500), min_size=3, max_size=3),
+       whole_chunks=st.booleans(), fk=st.lists(st.integers(-40, 40), min_size=3, max_size=3),
+       sk=st.integers(-64, 64), blocks=st.integers(1, 9), seed=st.integers(0, 2**31 - 1))
+def test_fuzz_k2_split_forms(form, n_facets, sizes, whole_chunks, fk, sk, blocks, seed):
+    """``extract_columns`` through the split K2 kernels that serve yN = 16384 on the GPU, forced
+    at yN = 512 (2 = 4 x Q with the L2 scratch, 3 = DIF / DIT with the L2 scratch, 4 / 5 / 6 = the
+    tensor-memory kernels: DIF with pair stores, DIT, DIT with the store phases half a line
+    apart): random facet counts and row lengths (whole 128-byte chunks -> swizzled tensor
+    loads, otherwise linear bulk copies; longer and shorter than yN / 2), offsets, and grid
+    sizes from one CTA walking every line to one line per CTA."""
+    import ctypes
+
+    import torch
+
+    W, N, xM, yN = 13.5625, 1024, 256, 512
+    if form not in _k2_cores:
+        _k2_cores[form] = (emu_core_class()(W, N, xM, yN, force_split=form), OracleCore(W, N, xM, yN))
+    core, oracle = _k2_cores[form]
+    core._lib.swiftly_b200_debug_max_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    core._lib.swiftly_b200_debug_max_blocks(core._plan, blocks * 16 if blocks == 9 else blocks)
+    rng = numpy.random.default_rng(seed)
+    Nx, Ny = core.subgrid_off_step, core.facet_off_step
+    fss = [(fs // 8) * 8 if whole_chunks else fs for fs in sizes[:n_facets]]
+    fss = [max(8, fs) for fs in fss]
+    offs = [k * Ny for k in fk[:n_facets]]
+    sg_off0 = sk * Nx
+    bfs = [pc.rand_c(rng, yN, fs) for fs in fss]
+    refs = [oracle.prepare_facet(oracle.extract_from_facet(bf, sg_off0, axis=0), off1, axis=1)
+            for bf, off1 in zip(bfs, offs)]
+    outs = core.extract_columns([torch.from_numpy(bf.copy()) for bf in bfs], sg_off0, offs)
+    for o, r in zip(outs, refs):
+        assert numpy.abs(o.numpy() - r).max() <= 1e-11 * numpy.abs(r).max()
